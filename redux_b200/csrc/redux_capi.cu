@@ -1,0 +1,758 @@
+// redux_capi.cu -- C ABI (include/redux_b200.h) + the block-batching host front end.
+//
+// Replaces, for in-memory streams, redux::compress / redux::decompress (src/lib.rs:102-120) and
+// the constructors that feed them (src/model/mod.rs:63, adaptive_linear.rs:21, adaptive_tree.rs:36).
+// There is deliberately no CPU path in this file: without a CUDA device every computing entry
+// point returns REDUX_CUDA_ERROR.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/redux_b200.h"
+#include "redux_batch_kernels.cuh"
+#include "redux_common.cuh"
+#include "redux_lane_codec.cuh"
+
+using namespace rdx;
+
+namespace {
+
+struct MagicEntry { int cls; uint32_t nbits; uint32_t len; void *ptr; };
+
+// Grow-only device buffer.
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + (bytes >> 3);          // 12.5% headroom against regrowth
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct DeviceState {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf slots, sizes, flag;                 // encoder workspace
+    DevBuf st_in, st_off, st_out, st_ooff, st_status, st_aux0, st_aux1, st_roff;   // host-API staging
+    uint8_t *text_lut = nullptr;
+    std::vector<MagicEntry> magics;
+    bool smem_set = false;
+};
+
+}  // namespace
+
+struct TimedSpan { cudaEvent_t a, b; int kind; int device; };
+
+struct redux_ctx {
+    std::vector<DeviceState> devs;
+    int sched = REDUX_SCHED_AUTO;
+    std::string last_error;
+    uint64_t launches = 0;
+    bool timing = false;                  // bracket every kernel with CUDA events (bench.py)
+    std::vector<TimedSpan> spans;
+};
+
+namespace {
+
+int fail(redux_ctx *ctx, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (ctx) {
+        char buf[512];
+        if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        else snprintf(buf, sizeof buf, "%s", what);
+        ctx->last_error = buf;
+    }
+    return code;
+}
+
+#define CU_TRY(ctx, expr)                                                             \
+    do { cudaError_t e__ = (expr);                                                    \
+         if (e__ != cudaSuccess) { (void)cudaGetLastError();                          \
+             return fail((ctx), REDUX_CUDA_ERROR, #expr, e__); } } while (0)
+
+DeviceState *find_dev(redux_ctx *ctx, int device)
+{
+    for (auto &d : ctx->devs) if (d.device == device) return &d;
+    return nullptr;
+}
+
+template <typename K>
+cudaError_t allow_smem(K kernel, size_t bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+cudaError_t configure_kernels()
+{
+    const size_t s16 = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * 2, s32 = s16 * 2;
+    cudaError_t e;
+#define RDX_CFG(K, BYTES) if ((e = allow_smem(K, BYTES)) != cudaSuccess) return e;
+    RDX_CFG((encode_lane_kernel<uint16_t, kNarrow>), s16) RDX_CFG((encode_lane_kernel<uint32_t, kNarrow>), s32)
+    RDX_CFG((encode_lane_kernel<uint16_t, kWide>), s16)   RDX_CFG((encode_lane_kernel<uint32_t, kWide>), s32)
+    RDX_CFG((encode_lane_kernel<uint16_t, kHuge>), s16)   RDX_CFG((encode_lane_kernel<uint32_t, kHuge>), s32)
+    RDX_CFG((decode_lane_kernel<uint16_t, kNarrow>), s16) RDX_CFG((decode_lane_kernel<uint32_t, kNarrow>), s32)
+    RDX_CFG((decode_lane_kernel<uint16_t, kWide>), s16)   RDX_CFG((decode_lane_kernel<uint32_t, kWide>), s32)
+    RDX_CFG((decode_lane_kernel<uint16_t, kHuge>), s16)   RDX_CFG((decode_lane_kernel<uint32_t, kHuge>), s32)
+#undef RDX_CFG
+    return cudaSuccess;
+}
+
+// Shape of one launch derived from the parameters and the longest block.
+struct Plan {
+    int cls; uint32_t f, c, tcap; bool wide_table; uint32_t magic_len; uint64_t slot_stride;
+};
+
+int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, Plan *pl)
+{
+    if (!p) return fail(ctx, REDUX_INVALID_INPUT, "params is NULL");
+    if (!params_valid(p->symbol_bits, p->freq_bits, p->code_bits))
+        return fail(ctx, REDUX_INVALID_INPUT, "Parameters::new rejects these parameters");
+    if (p->symbol_bits != (uint32_t)kSymbolBits)
+        return fail(ctx, REDUX_UNSUPPORTED, "device path implements symbol_bits == 8 only");
+    if (max_block_len > 0xFFFFFFF0ull)
+        return fail(ctx, REDUX_UNSUPPORTED, "blocks longer than 2^32-16 bytes are not supported");
+    pl->f = p->freq_bits; pl->c = p->code_bits;
+    pl->cls = arith_class(pl->f, pl->c);
+    const uint64_t fmax = ((uint64_t)1 << pl->f) - 1;
+    pl->tcap = (uint32_t)(fmax - kNsym);                       // f <= 31 -> fits
+    const uint64_t updates = std::min<uint64_t>(max_block_len, pl->tcap);
+    pl->wide_table = updates > 65536;                          // u16 increments suffice otherwise
+    pl->magic_len = (uint32_t)updates + 1;
+    const uint64_t bound = redux_compress_bound(max_block_len, pl->c);
+    pl->slot_stride = ((bound + 15) & ~(uint64_t)15) + 16;
+    return REDUX_OK;
+}
+
+int get_magic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const Plan &pl, const void **out)
+{
+    *out = nullptr;
+    if (pl.cls == kHuge) return REDUX_OK;
+    const uint32_t nbits = pl.f + pl.c;
+    for (auto &m : d->magics)
+        if (m.cls == pl.cls && m.nbits == nbits && m.len >= pl.magic_len) { *out = m.ptr; return REDUX_OK; }
+    const size_t esz = pl.cls == kNarrow ? sizeof(Magic32) : sizeof(Magic64);
+    const uint32_t len = std::max<uint32_t>(pl.magic_len, 1024);
+    void *ptr = nullptr;
+    CU_TRY(ctx, cudaMalloc(&ptr, esz * len));
+    const uint32_t threads = 256, grid = (len + threads - 1) / threads;
+    if (pl.cls == kNarrow) build_magic_kernel<Magic32><<<grid, threads, 0, stream>>>((Magic32 *)ptr, len, nbits);
+    else                   build_magic_kernel<Magic64><<<grid, threads, 0, stream>>>((Magic64 *)ptr, len, nbits);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    // the table must be visible to work on any stream of this device
+    CU_TRY(ctx, cudaStreamSynchronize(stream));
+    d->magics.push_back({pl.cls, nbits, len, ptr});
+    *out = ptr;
+    return REDUX_OK;
+}
+
+template <typename TW>
+void launch_encode(int cls, const LaneEncJob &job, uint32_t grid, size_t smem, cudaStream_t s)
+{
+    if (cls == kNarrow)    encode_lane_kernel<TW, kNarrow><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (cls == kWide) encode_lane_kernel<TW, kWide><<<grid, kLaneThreads, smem, s>>>(job);
+    else                   encode_lane_kernel<TW, kHuge><<<grid, kLaneThreads, smem, s>>>(job);
+}
+template <typename TW>
+void launch_decode(int cls, const LaneDecJob &job, uint32_t grid, size_t smem, cudaStream_t s)
+{
+    if (cls == kNarrow)    decode_lane_kernel<TW, kNarrow><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (cls == kWide) decode_lane_kernel<TW, kWide><<<grid, kLaneThreads, smem, s>>>(job);
+    else                   decode_lane_kernel<TW, kHuge><<<grid, kLaneThreads, smem, s>>>(job);
+}
+
+int check_kind(redux_ctx *ctx, int kind)
+{
+    if (kind != REDUX_MODEL_LINEAR && kind != REDUX_MODEL_TREE)
+        return fail(ctx, REDUX_INVALID_INPUT, "unknown model kind");
+    return REDUX_OK;
+}
+
+// RAII device switch
+struct DeviceGuard {
+    int prev = -1; bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; (void)cudaGetLastError(); }
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Brackets one kernel launch with events on the launching stream when ctx->timing is on.
+struct KernelTimer {
+    redux_ctx *ctx; cudaStream_t s; TimedSpan span; bool on;
+    KernelTimer(redux_ctx *c, int device, cudaStream_t st, int kind) : ctx(c), s(st), on(c->timing) {
+        if (!on) return;
+        span.kind = kind; span.device = device;
+        if (cudaEventCreate(&span.a) != cudaSuccess || cudaEventCreate(&span.b) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(span.a, s);
+    }
+    ~KernelTimer() { if (on) { cudaEventRecord(span.b, s); ctx->spans.push_back(span); } }
+};
+
+}  // namespace
+
+// =============================================================================== host arithmetic
+
+extern "C" int redux_parameters_new(uint32_t s, uint32_t f, uint32_t c, redux_parameters_t *o)
+{
+    if (!params_valid(s, f, c)) return REDUX_INVALID_INPUT;        // src/model/mod.rs:64-65
+    if (o) {
+        o->symbol_bits = s; o->symbol_eof = (uint64_t)1 << s; o->symbol_count = ((uint64_t)1 << s) + 1;
+        o->freq_bits = f;   o->freq_max = ((uint64_t)1 << f) - 1;
+        o->code_bits = c;   o->code_min = 0;
+        o->code_one_fourth = (uint64_t)1 << (c - 2);
+        o->code_half = (uint64_t)2 << (c - 2);
+        o->code_three_fourths = (uint64_t)3 << (c - 2);
+        o->code_max = ((uint64_t)1 << c) - 1;
+    }
+    return REDUX_OK;
+}
+
+extern "C" int redux_params_supported(const redux_params_t *p)
+{
+    if (!p || !params_valid(p->symbol_bits, p->freq_bits, p->code_bits)) return REDUX_INVALID_INPUT;
+    return p->symbol_bits == (uint32_t)kSymbolBits ? REDUX_OK : REDUX_UNSUPPORTED;
+}
+
+extern "C" const char *redux_error_string(int code)
+{
+    switch (code) {
+    case REDUX_OK: return "OK";
+    case REDUX_EOF: return "Unexpected end of file";                          // src/lib.rs:69
+    case REDUX_INVALID_INPUT: return "Invalid data found while processing input";  // src/lib.rs:70
+    case REDUX_IO_ERROR: return "I/O error";                                  // src/lib.rs:71
+    case REDUX_CUDA_ERROR: return "CUDA error";
+    case REDUX_UNSUPPORTED: return "Parameters not supported by the device path";
+    case REDUX_OUT_CAPACITY: return "Output buffer too small";
+    default: return "Unknown error";
+    }
+}
+
+extern "C" uint64_t redux_compress_bound(uint64_t in_len, uint32_t code_bits)
+{
+    return ((in_len + 1) * (uint64_t)code_bits + 7) / 8;
+}
+
+extern "C" int redux_debug_magic(uint64_t d, uint32_t nbits, int wide, uint64_t *magic, uint32_t *shift)
+{
+    if (d < 1 || d >> 32) return REDUX_INVALID_INPUT;
+    if (wide) { if (nbits > 62) return REDUX_INVALID_INPUT; Magic64 g = make_magic64(d, nbits); *magic = g.m; *shift = g.sh; }
+    else      { if (nbits > 30) return REDUX_INVALID_INPUT; Magic32 g = make_magic32((uint32_t)d, nbits); *magic = g.m; *shift = g.sh; }
+    return REDUX_OK;
+}
+
+extern "C" uint64_t redux_debug_magic_divide(uint64_t n, uint64_t magic, uint32_t shift, int wide)
+{
+    if (wide) { Magic64 g{magic, shift, 0}; return div_magic64(n, g); }
+    Magic32 g{(uint32_t)magic, shift};
+    return div_magic32((uint32_t)n, g);
+}
+
+extern "C" void redux_debug_renorm(uint64_t low, uint64_t high, uint32_t c, uint32_t *n1, uint32_t *k,
+                                   uint64_t *nl, uint64_t *nh)
+{
+    if (c <= 32) { Renorm<uint32_t> r = renorm<uint32_t>((uint32_t)low, (uint32_t)high, c); *n1 = r.n1; *k = r.k; *nl = r.low; *nh = r.high; }
+    else         { Renorm<uint64_t> r = renorm<uint64_t>(low, high, c); *n1 = r.n1; *k = r.k; *nl = r.low; *nh = r.high; }
+}
+
+extern "C" void redux_generate_blocks_host(uint8_t *out, uint64_t first_block, uint64_t n_blocks,
+                                           uint64_t block_len, uint64_t seed)
+{
+    uint8_t lut[256];
+    for (uint32_t u = 0; u < 256; ++u) lut[u] = text_symbol(u);
+    const uint64_t groups = (block_len + 7) >> 3;
+    for (uint64_t b = 0; b < n_blocks; ++b)
+        for (uint64_t w = 0; w < groups; ++w) {
+            uint64_t v = gen_group(seed, first_block + b, w, lut);
+            for (uint64_t j = 0; j < 8 && w * 8 + j < block_len; ++j)
+                out[b * block_len + w * 8 + j] = (uint8_t)(v >> (8 * j));
+        }
+}
+
+// ======================================================================================= context
+
+extern "C" int redux_ctx_create(const int *devices, int n_devices, redux_ctx_t **out)
+{
+    if (!out) return REDUX_INVALID_INPUT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { (void)cudaGetLastError(); return REDUX_CUDA_ERROR; }
+    redux_ctx *ctx = new redux_ctx();
+    std::vector<int> devs;
+    if (!devices || n_devices <= 0) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) { delete ctx; return REDUX_CUDA_ERROR; }
+        devs.push_back(cur);
+    } else {
+        devs.assign(devices, devices + n_devices);
+    }
+    uint8_t lut[256];
+    for (uint32_t u = 0; u < 256; ++u) lut[u] = text_symbol(u);
+    for (int dev : devs) {
+        if (dev < 0 || dev >= count) { redux_ctx_destroy(ctx); return REDUX_INVALID_INPUT; }
+        DeviceGuard g(dev);
+        DeviceState d;
+        d.device = dev;
+        cudaDeviceProp prop;
+        if (!g.ok || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { redux_ctx_destroy(ctx); return REDUX_CUDA_ERROR; }
+        if (prop.major < 10) { redux_ctx_destroy(ctx); return REDUX_CUDA_ERROR; }   // sm_100a binary only
+        if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            configure_kernels() != cudaSuccess ||
+            cudaMalloc((void **)&d.text_lut, 256) != cudaSuccess ||
+            cudaMemcpy(d.text_lut, lut, 256, cudaMemcpyHostToDevice) != cudaSuccess) {
+            (void)cudaGetLastError();
+            ctx->devs.push_back(d);
+            redux_ctx_destroy(ctx);
+            return REDUX_CUDA_ERROR;
+        }
+        ctx->devs.push_back(d);
+    }
+    *out = ctx;
+    return REDUX_OK;
+}
+
+extern "C" void redux_ctx_destroy(redux_ctx_t *ctx)
+{
+    if (!ctx) return;
+    for (auto &d : ctx->devs) {
+        DeviceGuard g(d.device);
+        if (d.stream) { cudaStreamSynchronize(d.stream); cudaStreamDestroy(d.stream); }
+        for (DevBuf *b : {&d.slots, &d.sizes, &d.flag, &d.st_in, &d.st_off, &d.st_out, &d.st_ooff,
+                          &d.st_status, &d.st_aux0, &d.st_aux1, &d.st_roff}) b->release();
+        for (auto &m : d.magics) cudaFree(m.ptr);
+        if (d.text_lut) cudaFree(d.text_lut);
+    }
+    delete ctx;
+}
+
+extern "C" int redux_ctx_device_count(const redux_ctx_t *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+extern "C" const char *redux_ctx_last_error(const redux_ctx_t *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+extern "C" uint64_t redux_ctx_kernel_launches(const redux_ctx_t *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int redux_ctx_timing_enable(redux_ctx_t *ctx, int on)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    ctx->timing = on != 0;
+    return REDUX_OK;
+}
+
+extern "C" int redux_ctx_timing_collect(redux_ctx_t *ctx, double *ms, uint64_t *counts)
+{
+    if (!ctx || !ms || !counts) return REDUX_INVALID_INPUT;
+    for (int k = 0; k < REDUX_KERNEL_KINDS; ++k) { ms[k] = 0; counts[k] = 0; }
+    int rc = REDUX_OK;
+    for (auto &sp : ctx->spans) {
+        DeviceGuard g(sp.device);
+        float t = 0;
+        if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) {
+            ms[sp.kind] += t; counts[sp.kind] += 1;
+        } else { (void)cudaGetLastError(); rc = REDUX_CUDA_ERROR; }
+        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    ctx->spans.clear();
+    return rc;
+}
+
+extern "C" int redux_ctx_set_schedule(redux_ctx_t *ctx, int sched)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    if (sched == REDUX_SCHED_AUTO || sched == REDUX_SCHED_LANE) { ctx->sched = sched; return REDUX_OK; }
+    if (sched == REDUX_SCHED_WARP) return fail(ctx, REDUX_UNSUPPORTED, "warp schedule not built yet");
+    return fail(ctx, REDUX_INVALID_INPUT, "unknown schedule");
+}
+
+extern "C" int redux_ctx_synchronize(redux_ctx_t *ctx, int device, void *stream)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    DeviceState *d = find_dev(ctx, device);
+    if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
+    DeviceGuard g(device);
+    CU_TRY(ctx, cudaStreamSynchronize(stream ? (cudaStream_t)stream : d->stream));
+    return REDUX_OK;
+}
+
+// ============================================================================ device-resident API
+
+extern "C" int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *stream_, int model_kind,
+                                         const redux_params_t *params, const uint8_t *d_in,
+                                         const uint64_t *d_in_offsets, uint64_t n_blocks,
+                                         uint64_t max_block_len, uint8_t *d_out, uint64_t out_capacity,
+                                         uint64_t *d_out_offsets, int32_t *d_status)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    int rc;
+    if ((rc = check_kind(ctx, model_kind))) return rc;
+    Plan pl;
+    if ((rc = make_plan(ctx, params, max_block_len, &pl))) return rc;
+    DeviceState *d = find_dev(ctx, device);
+    if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
+    if (!d_in_offsets || !d_out_offsets || !d_status || (!d_out && out_capacity))
+        return fail(ctx, REDUX_INVALID_INPUT, "NULL buffer");
+    DeviceGuard g(device);
+    cudaStream_t s = stream_ ? (cudaStream_t)stream_ : d->stream;
+    if (n_blocks == 0) { CU_TRY(ctx, cudaMemsetAsync(d_out_offsets, 0, sizeof(uint64_t), s)); return REDUX_OK; }
+    if (n_blocks > 0x7FFFFFFFull * 32) return fail(ctx, REDUX_UNSUPPORTED, "too many blocks in one launch");
+
+    const void *magic = nullptr;
+    if ((rc = get_magic(ctx, d, s, pl, &magic))) return rc;
+    CU_TRY(ctx, d->slots.reserve(n_blocks * pl.slot_stride));
+    CU_TRY(ctx, d->sizes.reserve(n_blocks * sizeof(uint32_t)));
+    CU_TRY(ctx, d->flag.reserve(sizeof(int32_t)));
+
+    LaneEncJob job;
+    job.in = d_in; job.in_off = d_in_offsets; job.n_blocks = n_blocks;
+    job.slots = (uint8_t *)d->slots.p; job.slot_stride = pl.slot_stride;
+    job.sizes = (uint32_t *)d->sizes.p; job.status = d_status;
+    job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
+    const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
+    {
+        KernelTimer kt(ctx, device, s, REDUX_KERNEL_ENCODE);
+        if (pl.wide_table) launch_encode<uint32_t>(pl.cls, job, grid, smem, s);
+        else               launch_encode<uint16_t>(pl.cls, job, grid, smem, s);
+    }
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+
+    {
+        KernelTimer kt(ctx, device, s, REDUX_KERNEL_SCAN);
+        scan_sizes_kernel<<<1, kScanThreads, 0, s>>>(job.sizes, n_blocks, d_out_offsets, out_capacity,
+                                                     (int32_t *)d->flag.p);
+    }
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    const uint32_t cgrid = (uint32_t)std::min<uint64_t>(n_blocks, 148 * 16);
+    {
+        KernelTimer kt(ctx, device, s, REDUX_KERNEL_COMPACT);
+        compact_kernel<<<cgrid, kCompactThreads, 0, s>>>(job.slots, pl.slot_stride, job.sizes, d_out_offsets,
+                                                         n_blocks, d_out, out_capacity, d_status);
+    }
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return REDUX_OK;
+}
+
+extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *stream_, int model_kind,
+                                         const redux_params_t *params, const uint8_t *d_comp,
+                                         const uint64_t *d_comp_offsets, uint64_t n_blocks,
+                                         uint64_t max_block_len, uint8_t *d_raw,
+                                         const uint64_t *d_raw_offsets, uint64_t *d_raw_lens,
+                                         uint64_t *d_consumed, int32_t *d_status)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    int rc;
+    if ((rc = check_kind(ctx, model_kind))) return rc;
+    Plan pl;
+    if ((rc = make_plan(ctx, params, max_block_len, &pl))) return rc;
+    DeviceState *d = find_dev(ctx, device);
+    if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
+    if (n_blocks == 0) return REDUX_OK;
+    if (!d_comp_offsets || !d_raw_offsets || !d_raw_lens || !d_consumed || !d_status)
+        return fail(ctx, REDUX_INVALID_INPUT, "NULL buffer");
+    DeviceGuard g(device);
+    cudaStream_t s = stream_ ? (cudaStream_t)stream_ : d->stream;
+    const void *magic = nullptr;
+    if ((rc = get_magic(ctx, d, s, pl, &magic))) return rc;
+
+    LaneDecJob job;
+    job.comp = d_comp; job.comp_off = d_comp_offsets; job.n_blocks = n_blocks;
+    job.raw = d_raw; job.raw_off = d_raw_offsets; job.raw_len = d_raw_lens; job.consumed = d_consumed;
+    job.status = d_status; job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
+    const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
+    {
+        KernelTimer kt(ctx, device, s, REDUX_KERNEL_DECODE);
+        if (pl.wide_table) launch_decode<uint32_t>(pl.cls, job, grid, smem, s);
+        else               launch_decode<uint16_t>(pl.cls, job, grid, smem, s);
+    }
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return REDUX_OK;
+}
+
+extern "C" int redux_generate_blocks_device(redux_ctx_t *ctx, int device, void *stream_, uint8_t *d_out,
+                                            uint64_t first_block, uint64_t n_blocks, uint64_t block_len,
+                                            uint64_t seed)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    DeviceState *d = find_dev(ctx, device);
+    if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
+    if (n_blocks == 0 || block_len == 0) return REDUX_OK;
+    DeviceGuard g(device);
+    cudaStream_t s = stream_ ? (cudaStream_t)stream_ : d->stream;
+    {
+        KernelTimer kt(ctx, device, s, REDUX_KERNEL_GENERATE);
+        generate_kernel<<<148 * 8, 256, 0, s>>>(d_out, first_block, n_blocks, block_len, seed, d->text_lut);
+    }
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return REDUX_OK;
+}
+
+// ================================================================================ host-buffer API
+namespace {
+
+struct Shard { uint64_t first, count; };
+
+std::vector<Shard> make_shards(uint64_t n_blocks, size_t n_dev)
+{
+    // contiguous block-index ranges, SURVEY.md 8(e)
+    std::vector<Shard> s(n_dev);
+    for (size_t g = 0; g < n_dev; ++g) {
+        uint64_t a = n_blocks * g / n_dev, b = n_blocks * (g + 1) / n_dev;
+        s[g] = {a, b - a};
+    }
+    return s;
+}
+
+
+// Runs fn(view, device_state, g) for every shard: inline for one device, one host thread per device
+// otherwise.  Each worker gets a private view of the context (own error string / launch counter) so the
+// workers never share mutable state; the views are merged afterwards.
+template <typename F>
+void for_each_device(redux_ctx *ctx, size_t nd, std::vector<int> &rcs, F fn)
+{
+    if (nd == 1) { rcs[0] = fn(ctx, &ctx->devs[0], (size_t)0); return; }
+    std::vector<std::thread> th;
+    std::vector<std::string> errs(nd);
+    std::vector<uint64_t> launches(nd, 0);
+    std::vector<std::vector<TimedSpan>> spans(nd);
+    for (size_t g = 0; g < nd; ++g) th.emplace_back([&, g] {
+        redux_ctx view; view.sched = ctx->sched; view.timing = ctx->timing;
+        view.devs.push_back(ctx->devs[g]);
+        rcs[g] = fn(&view, &view.devs[0], g);
+        ctx->devs[g] = view.devs[0];          // workspaces may have grown
+        view.devs.clear();
+        errs[g] = view.last_error; launches[g] = view.launches; spans[g] = view.spans;
+    });
+    for (auto &t : th) t.join();
+    for (size_t g = 0; g < nd; ++g) {
+        ctx->launches += launches[g];
+        ctx->spans.insert(ctx->spans.end(), spans[g].begin(), spans[g].end());
+        if (rcs[g]) ctx->last_error = errs[g];
+    }
+}
+
+// Phase 1 of a shard: H2D, kernels, D2H of offsets + status. Leaves the compacted bytes on the device.
+int encode_shard_phase1(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t *p,
+                        const uint8_t *in, const uint64_t *in_off, Shard sh, uint64_t out_cap_hint,
+                        uint64_t *out_off_local, int32_t *status, uint64_t *total)
+{
+    DeviceGuard g(d->device);
+    cudaStream_t s = d->stream;
+    const uint64_t base = in_off[sh.first], bytes = in_off[sh.first + sh.count] - base;
+    uint64_t max_len = 0;
+    std::vector<uint64_t> rel(sh.count + 1);
+    for (uint64_t i = 0; i <= sh.count; ++i) {
+        rel[i] = in_off[sh.first + i] - base;
+        if (i) { if (rel[i] < rel[i - 1]) return fail(ctx, REDUX_INVALID_INPUT, "offsets not monotonic");
+                 max_len = std::max(max_len, rel[i] - rel[i - 1]); }
+    }
+    Plan pl;
+    int rc = make_plan(ctx, p, max_len, &pl);
+    if (rc) return rc;
+    uint64_t worst = 0;
+    for (uint64_t i = 0; i < sh.count; ++i) worst += redux_compress_bound(rel[i + 1] - rel[i], pl.c);
+    const uint64_t dcap = std::min(worst, out_cap_hint);
+    CU_TRY(ctx, d->st_in.reserve(bytes + 32));
+    CU_TRY(ctx, d->st_off.reserve((sh.count + 1) * sizeof(uint64_t)));
+    CU_TRY(ctx, d->st_out.reserve(dcap + 32));
+    CU_TRY(ctx, d->st_ooff.reserve((sh.count + 1) * sizeof(uint64_t)));
+    CU_TRY(ctx, d->st_status.reserve(sh.count * sizeof(int32_t)));
+    CU_TRY(ctx, cudaMemcpyAsync(d->st_in.p, in + base, bytes, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(d->st_off.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));   // rel is a stack-lifetime vector
+    rc = redux_encode_batch_device(ctx, d->device, s, kind, p, (const uint8_t *)d->st_in.p,
+                                   (const uint64_t *)d->st_off.p, sh.count, max_len, (uint8_t *)d->st_out.p,
+                                   dcap, (uint64_t *)d->st_ooff.p, (int32_t *)d->st_status.p);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(out_off_local, d->st_ooff.p, (sh.count + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(status, d->st_status.p, sh.count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    *total = out_off_local[sh.count];
+    return REDUX_OK;
+}
+
+}  // namespace
+
+extern "C" int redux_encode_batch(redux_ctx_t *ctx, int model_kind, const redux_params_t *params,
+                                  const uint8_t *in, const uint64_t *in_offsets, uint64_t n_blocks,
+                                  uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets, int32_t *status)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    int rc;
+    if ((rc = check_kind(ctx, model_kind))) return rc;
+    Plan probe;
+    if ((rc = make_plan(ctx, params, 0, &probe))) return rc;
+    if (!in_offsets || !out_offsets || (n_blocks && !status)) return fail(ctx, REDUX_INVALID_INPUT, "NULL buffer");
+    out_offsets[0] = 0;
+    if (n_blocks == 0) return REDUX_OK;
+
+    const size_t nd = std::min<uint64_t>(ctx->devs.size(), n_blocks);
+    std::vector<Shard> shards = make_shards(n_blocks, nd);
+    std::vector<std::vector<uint64_t>> local(nd);
+    std::vector<uint64_t> totals(nd, 0);
+    std::vector<int> rcs(nd, REDUX_OK);
+    for (size_t g = 0; g < nd; ++g) local[g].resize(shards[g].count + 1);
+    for_each_device(ctx, nd, rcs, [&](redux_ctx *view, DeviceState *d, size_t g) {
+        return encode_shard_phase1(view, d, model_kind, params, in, in_offsets, shards[g], out_capacity,
+                                   local[g].data(), status + shards[g].first, &totals[g]);
+    });
+    for (size_t g = 0; g < nd; ++g) if (rcs[g]) return rcs[g];
+
+    // global offsets, then phase 2: D2H of each shard's bytes to its place
+    uint64_t base = 0;
+    std::vector<uint64_t> bases(nd);
+    for (size_t g = 0; g < nd; ++g) {
+        bases[g] = base;
+        for (uint64_t i = 0; i <= shards[g].count; ++i) out_offsets[shards[g].first + i] = base + local[g][i];
+        base += totals[g];
+    }
+    if (base > out_capacity) {
+        // streams that do not fit were not compacted (status 6 where the device saw it); a shard whose
+        // global placement overflows is reported here
+        for (size_t g = 0; g < nd; ++g)
+            for (uint64_t i = 0; i < shards[g].count; ++i)
+                if (out_offsets[shards[g].first + i + 1] > out_capacity) status[shards[g].first + i] = REDUX_OUT_CAPACITY;
+        return fail(ctx, REDUX_OUT_CAPACITY, "output buffer too small for the compressed batch");
+    }
+    for (size_t g = 0; g < nd; ++g) {
+        DeviceState &d = ctx->devs[g];
+        DeviceGuard gd(d.device);
+        if (totals[g]) CU_TRY(ctx, cudaMemcpyAsync(out + bases[g], d.st_out.p, totals[g], cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (size_t g = 0; g < nd; ++g) {
+        DeviceGuard gd(ctx->devs[g].device);
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->devs[g].stream));
+    }
+    for (uint64_t i = 0; i < n_blocks; ++i) if (status[i]) return status[i];
+    return REDUX_OK;
+}
+
+namespace {
+
+int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t *p, const uint8_t *comp,
+                 const uint64_t *comp_off, Shard sh, uint8_t *raw, const uint64_t *raw_off,
+                 uint64_t *raw_lens, uint64_t *consumed, int32_t *status)
+{
+    DeviceGuard g(d->device);
+    cudaStream_t s = d->stream;
+    const uint64_t cbase = comp_off[sh.first], cbytes = comp_off[sh.first + sh.count] - cbase;
+    const uint64_t rbase = raw_off[sh.first], rbytes = raw_off[sh.first + sh.count] - rbase;
+    std::vector<uint64_t> crel(sh.count + 1), rrel(sh.count + 1);
+    uint64_t max_len = 0;
+    for (uint64_t i = 0; i <= sh.count; ++i) {
+        crel[i] = comp_off[sh.first + i] - cbase;
+        rrel[i] = raw_off[sh.first + i] - rbase;
+        if (i) {
+            if (crel[i] < crel[i - 1] || rrel[i] < rrel[i - 1]) return fail(ctx, REDUX_INVALID_INPUT, "offsets not monotonic");
+            max_len = std::max(max_len, rrel[i] - rrel[i - 1]);
+        }
+    }
+    CU_TRY(ctx, d->st_in.reserve(cbytes + 32));
+    CU_TRY(ctx, d->st_off.reserve((sh.count + 1) * sizeof(uint64_t)));
+    CU_TRY(ctx, d->st_roff.reserve((sh.count + 1) * sizeof(uint64_t)));
+    CU_TRY(ctx, d->st_out.reserve(rbytes + 32));
+    CU_TRY(ctx, d->st_aux0.reserve(sh.count * sizeof(uint64_t)));
+    CU_TRY(ctx, d->st_aux1.reserve(sh.count * sizeof(uint64_t)));
+    CU_TRY(ctx, d->st_status.reserve(sh.count * sizeof(int32_t)));
+    CU_TRY(ctx, cudaMemcpyAsync(d->st_in.p, comp + cbase, cbytes, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(d->st_off.p, crel.data(), crel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemcpyAsync(d->st_roff.p, rrel.data(), rrel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    int rc = redux_decode_batch_device(ctx, d->device, s, kind, p, (const uint8_t *)d->st_in.p,
+                                       (const uint64_t *)d->st_off.p, sh.count, max_len, (uint8_t *)d->st_out.p,
+                                       (const uint64_t *)d->st_roff.p, (uint64_t *)d->st_aux0.p,
+                                       (uint64_t *)d->st_aux1.p, (int32_t *)d->st_status.p);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(raw_lens + sh.first, d->st_aux0.p, sh.count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(consumed + sh.first, d->st_aux1.p, sh.count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(status + sh.first, d->st_status.p, sh.count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    // copy back only what was decoded: contiguous when every slot is full (the usual case), else per block
+    bool full = true;
+    for (uint64_t i = 0; i < sh.count && full; ++i) full = raw_lens[sh.first + i] == rrel[i + 1] - rrel[i];
+    if (full) {
+        if (rbytes) CU_TRY(ctx, cudaMemcpyAsync(raw + rbase, d->st_out.p, rbytes, cudaMemcpyDeviceToHost, s));
+    } else {
+        for (uint64_t i = 0; i < sh.count; ++i) {
+            const uint64_t n = raw_lens[sh.first + i];
+            if (n) CU_TRY(ctx, cudaMemcpyAsync(raw + rbase + rrel[i], (const uint8_t *)d->st_out.p + rrel[i], n,
+                                               cudaMemcpyDeviceToHost, s));
+        }
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+    return REDUX_OK;
+}
+
+}  // namespace
+
+extern "C" int redux_decode_batch(redux_ctx_t *ctx, int model_kind, const redux_params_t *params,
+                                  const uint8_t *comp, const uint64_t *comp_offsets, uint64_t n_blocks,
+                                  uint8_t *raw, const uint64_t *raw_offsets, uint64_t *raw_lens,
+                                  uint64_t *consumed, int32_t *status)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    int rc;
+    if ((rc = check_kind(ctx, model_kind))) return rc;
+    Plan probe;
+    if ((rc = make_plan(ctx, params, 0, &probe))) return rc;
+    if (n_blocks == 0) return REDUX_OK;
+    if (!comp_offsets || !raw_offsets || !raw_lens || !consumed || !status)
+        return fail(ctx, REDUX_INVALID_INPUT, "NULL buffer");
+    const size_t nd = std::min<uint64_t>(ctx->devs.size(), n_blocks);
+    std::vector<Shard> shards = make_shards(n_blocks, nd);
+    std::vector<int> rcs(nd, REDUX_OK);
+    for_each_device(ctx, nd, rcs, [&](redux_ctx *view, DeviceState *d, size_t g) {
+        return decode_shard(view, d, model_kind, params, comp, comp_offsets, shards[g], raw, raw_offsets,
+                            raw_lens, consumed, status);
+    });
+    for (size_t g = 0; g < nd; ++g) if (rcs[g]) return rcs[g];
+    for (uint64_t i = 0; i < n_blocks; ++i) if (status[i]) return status[i];
+    return REDUX_OK;
+}
+
+// ================================================================================== single stream
+
+extern "C" int redux_compress(redux_ctx_t *ctx, int model_kind, const redux_params_t *params,
+                              const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_capacity,
+                              uint64_t *in_count, uint64_t *out_count)
+{
+    if (in_count) *in_count = 0;
+    if (out_count) *out_count = 0;
+    uint64_t in_off[2] = {0, in_len}, out_off[2] = {0, 0};
+    int32_t st = 0;
+    int rc = redux_encode_batch(ctx, model_kind, params, in, in_off, 1, out, out_capacity, out_off, &st);
+    if (rc == REDUX_OK || rc == REDUX_OUT_CAPACITY) {
+        if (in_count) *in_count = in_len;                 // BitReader::get_count (src/lib.rs:108)
+        if (out_count) *out_count = out_off[1];           // BitWriter::get_count
+    }
+    return rc;
+}
+
+extern "C" int redux_decompress(redux_ctx_t *ctx, int model_kind, const redux_params_t *params,
+                                const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_capacity,
+                                uint64_t *in_count, uint64_t *out_count)
+{
+    if (in_count) *in_count = 0;
+    if (out_count) *out_count = 0;
+    uint64_t comp_off[2] = {0, in_len}, raw_off[2] = {0, out_capacity}, raw_len = 0, consumed = 0;
+    int32_t st = 0;
+    int rc = redux_decode_batch(ctx, model_kind, params, in, comp_off, 1, out, raw_off, &raw_len, &consumed, &st);
+    if (rc == REDUX_OK || rc == REDUX_EOF || rc == REDUX_OUT_CAPACITY) {
+        if (in_count) *in_count = consumed;
+        if (out_count) *out_count = raw_len;
+    }
+    return rc;
+}

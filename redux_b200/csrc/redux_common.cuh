@@ -1,0 +1,204 @@
+// redux_common.cuh -- shared host/device arithmetic of the B200 coder.
+//
+// Everything here is written from the algorithm's definition, not from the
+// reference's code shape: the reference renormalises bit by bit and divides by the running total
+// (src/codec.rs:58-89); the device path uses the closed forms below, and tests/ prove them equal
+// to the loop on the oracle.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RDX_HD __host__ __device__ __forceinline__
+#else
+#define RDX_HD inline
+#endif
+
+namespace rdx {
+
+constexpr int kSymbolBits = 8;          // device path scope: byte symbols
+constexpr uint32_t kEof = 256;          // Parameters::symbol_eof   (src/model/mod.rs:69)
+constexpr uint32_t kNsym = 257;         // Parameters::symbol_count (src/model/mod.rs:70)
+
+// Arithmetic class of a (freq_bits, code_bits) pair.
+//   NARROW: code+freq <= 30 -> every product fits 32 bits, 32-bit magic division.
+//   WIDE  : code <= 32      -> 32-bit coder state, 64-bit products, 64-bit magic division.
+//   HUGE  : code  > 32      -> 64-bit coder state, products < 2^64 (code+freq <= 64), hardware-less
+//                              64-bit division (rare parameter corner; correctness only).
+enum ArithClass { kNarrow = 0, kWide = 1, kHuge = 2 };
+
+RDX_HD int arith_class(uint32_t f, uint32_t c) {
+    return (c + f <= 30) ? kNarrow : (c <= 32 ? kWide : kHuge);
+}
+
+// Parameters::new validation (src/model/mod.rs:64), identical rejection rule.
+RDX_HD bool params_valid(uint64_t s, uint64_t f, uint64_t c) {
+    return !(s < 1 || f < s + 2 || c < f + 2 || 64 < c + f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// count reciprocal.  The coder divides by count_t = min(NSYM + t, FMAX): a pure
+// function of the symbol position t, identical for every stream.  floor(n / d) for n < 2^nbits is
+// computed as mulhi(n, magic) >> shift with
+//     l = ceil(log2 d),  S = max(W, nbits + l),  magic = floor(2^S / d) + 1,  shift = S - W
+// (W = 32 or 64).  Exact because e = magic*d - 2^S lies in [1, d] <= 2^l <= 2^(S-nbits), so the
+// error term n*e/(d*2^S) < 1/d never carries the quotient over an integer.
+// magic < 2^W needs nbits + 1 <= W - 1, i.e. nbits <= 30 (W=32) / nbits <= 62 (W=64).
+// ---------------------------------------------------------------------------------------------
+struct Magic32 { uint32_t m; uint32_t sh; };
+struct Magic64 { uint64_t m; uint32_t sh; uint32_t pad; };
+
+RDX_HD uint32_t ceil_log2_u64(uint64_t d) {
+    uint32_t l = 0;
+    while (l < 64 && ((uint64_t)1 << l) < d) ++l;
+    return l;
+}
+
+// Long division of 2^S by d (d < 2^32, S <= 126) -> floor(2^S/d) truncated to 64 bits.
+// Only called with quotients that fit (see above).  Bit-serial restoring division: runs once per
+// table entry at set-up time, never on the coding path.
+RDX_HD uint64_t pow2_div(uint32_t S, uint64_t d) {
+    uint64_t q = 0, r = 0;
+    // dividend = 1 followed by S zero bits; feed bits MSB first
+    for (int i = (int)S; i >= 0; --i) {
+        r = (r << 1) | (i == (int)S ? 1u : 0u);
+        q <<= 1;
+        if (r >= d) { r -= d; q |= 1; }
+    }
+    return q;
+}
+
+RDX_HD Magic32 make_magic32(uint32_t d, uint32_t nbits) {
+    uint32_t l = ceil_log2_u64(d);
+    uint32_t S = nbits + l; if (S < 32) S = 32;
+    Magic32 r; r.m = (uint32_t)(pow2_div(S, d) + 1); r.sh = S - 32;
+    return r;
+}
+RDX_HD Magic64 make_magic64(uint64_t d, uint32_t nbits) {
+    uint32_t l = ceil_log2_u64(d);
+    uint32_t S = nbits + l; if (S < 64) S = 64;
+    Magic64 r; r.m = pow2_div(S, d) + 1; r.sh = S - 64; r.pad = 0;
+    return r;
+}
+
+RDX_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+RDX_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+RDX_HD uint32_t div_magic32(uint32_t n, Magic32 g) { return mulhi32(n, g.m) >> g.sh; }
+RDX_HD uint64_t div_magic64(uint64_t n, Magic64 g) { return mulhi64(n, g.m) >> g.sh; }
+
+RDX_HD int clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+RDX_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Renormalisation closed form.  Given the narrowed interval [low, high] in a c-bit
+// register: n1 = number of leading bits low and high share (the E1/E2 shifts of src/codec.rs:63-74,
+// each emitting that bit), then k = length of the run, starting just below the MSB, where low has 1
+// and high has 0 (the E3 shifts of :75-83).  E1/E2 can never follow an E3 inside one symbol, so
+// the whole loop is (n1, k).  T = uint32_t (c <= 32) or uint64_t (c <= 61).
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Renorm { T low, high; uint32_t n1, k; };
+
+template <typename T>
+RDX_HD Renorm<T> renorm(T low, T high, uint32_t c) {
+    constexpr int W = sizeof(T) * 8;
+    const T maxv = (c == (uint32_t)W) ? ~(T)0 : ((((T)1) << c) - 1);
+    T x = low ^ high;
+    int lz = (W == 32) ? clz32((uint32_t)x) : clz64((uint64_t)x);
+    uint32_t n1 = (uint32_t)lz - (uint32_t)(W - c);           // x == 0 -> lz == W -> n1 == c
+    // shift out the n1 common bits; high refills with ones (src/codec.rs:87-88)
+    T l1, h1;
+    if (n1 >= (uint32_t)W) { l1 = 0; h1 = maxv; }
+    else {
+        l1 = (T)(low << n1) & maxv;
+        h1 = (T)((high << n1) | ((((T)1) << n1) - 1)) & maxv;
+    }
+    // E3 run: bits c-2 downwards with low=1, high=0
+    T z = (T)(l1 & ~h1) << (W + 1 - c);                       // bit c-2 -> bit W-1; low bits zero
+    T nz = ~z;                                                // has a 1 in its low (W+1-c) >= 1 bits
+    uint32_t k = (uint32_t)((W == 32) ? clz32((uint32_t)nz) : clz64((uint64_t)nz));
+    const T body = maxv >> 1;                                 // bits below the MSB
+    const T half = body + 1;
+    Renorm<T> r;
+    r.n1 = n1; r.k = k;
+    r.low = (T)(l1 << k) & body;                              // MSB of low stays 0
+    r.high = ((T)((h1 << k) | ((((T)1) << k) - 1)) & body) | half;   // MSB of high stays 1
+    if (n1 == c) { r.low = 0; r.high = maxv; }                // degenerate low==high: k == 0 already
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic mixed-entropy blocks (BASELINE.json configs 3-4).  Counter-based splitmix64 so that the
+// GPU can fill any 8-byte group independently: draw(block, w) = mix(seed + block*K + (w+1)*GAMMA).
+// class = block & 3:
+//   0 uniform bytes                                   H ~ 8.0  bit/byte
+//   1 text-like: 256-entry Zipf table over 55 symbols H ~ 4.5
+//   2 geometric: ctz of a 16-bit field                H ~ 2.0
+//   3 sparse: 0x00 with p = 63/64, else a random byte H ~ 0.24
+// (the reference's corpora cannot travel to the GPU box, so class 1 is a table-driven stand-in for
+// the "corpus window" class of SURVEY.md 8(d); order-0 statistics are what an order-0 coder sees.)
+// ---------------------------------------------------------------------------------------------
+RDX_HD uint64_t splitmix_mix(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+RDX_HD uint64_t gen_draw(uint64_t seed, uint64_t block, uint64_t w) {
+    return splitmix_mix(seed + block * 0xD1342543DE82EF95ull + (w + 1) * 0x9E3779B97F4A7C15ull);
+}
+// text-like table: rank r owns max(1, 60/(r+1)) of the 256 slots (integer Zipf law; the slots run
+// out at rank 54, order-0 entropy 4.53 bit/byte -- calgary/book1 measures 4.527).
+RDX_HD uint8_t text_symbol(uint32_t u8v) {
+    const char *alphabet = " etaoinshrdlucmfwypvbgk,.\n-'\";ETAOINSHRDLUCMFWYPVBGKjxqz0123456";
+    uint32_t acc = 0;
+    for (uint32_t r = 0; r < 64; ++r) {
+        uint32_t n = 60 / (r + 1); if (n < 1) n = 1;
+        acc += n;
+        if (u8v < acc) return (uint8_t)alphabet[r];
+    }
+    return (uint8_t)alphabet[63];
+}
+// 8 output bytes for 64-bit group w of `block`
+RDX_HD uint64_t gen_group(uint64_t seed, uint64_t block, uint64_t w, const uint8_t *text_lut) {
+    uint64_t r = gen_draw(seed, block, w);
+    uint32_t cls = (uint32_t)(block & 3);
+    if (cls == 0) return r;
+    uint64_t out = 0;
+    if (cls == 1) {
+        for (int j = 0; j < 8; ++j) out |= (uint64_t)text_lut[(r >> (8 * j)) & 255] << (8 * j);
+        return out;
+    }
+    uint64_t r2 = splitmix_mix(r ^ 0xA5A5A5A5A5A5A5A5ull);
+    for (int j = 0; j < 8; ++j) {
+        uint32_t u = (uint32_t)(((j < 4 ? r : r2) >> (16 * (j & 3))) & 0xFFFF);
+        uint32_t b;
+        if (cls == 2) { uint32_t v = u | 0x8000u; b = 0; while (!(v & 1)) { v >>= 1; ++b; } }
+        else          { b = (u < 0xFC00u) ? 0u : (u & 0xFFu); }
+        out |= (uint64_t)b << (8 * j);
+    }
+    return out;
+}
+
+}  // namespace rdx

@@ -1,0 +1,196 @@
+"""C-ABI library checks that need no GPU: it loads, exports every symbol include/redux_b200.h declares,
+and its host-side arithmetic (Parameters, count reciprocals, closed-form renormalisation, generator)
+agrees with the oracle / the reference's loop."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as o
+import redux_b200 as rb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "redux_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(redux_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    L = rb.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_error_strings_match_reference_display():
+    """src/lib.rs:66-73."""
+    L = rb.lib()
+    assert L.redux_error_string(rb.EOF) == b"Unexpected end of file"
+    assert L.redux_error_string(rb.INVALID_INPUT) == b"Invalid data found while processing input"
+    assert L.redux_error_string(rb.IO_ERROR).startswith(b"I/O error")
+
+
+def test_parameters_new_matches_oracle_everywhere():
+    """Same acceptance set and same derived constants as Parameters::new (src/model/mod.rs:63-81)."""
+    for s in range(0, 14):
+        for f in range(0, 36):
+            for c in range(0, 66, 1):
+                rc, p = o.params_new(s, f, c)
+                try:
+                    q = rb.Parameters(s, f, c)
+                    ok = True
+                except rb.InvalidInput:
+                    ok = False
+                assert ok == (rc == o.OK), (s, f, c)
+                if ok:
+                    for name, _ in o.Params._fields_:
+                        assert getattr(q, name) == getattr(p, name), (s, f, c, name)
+
+
+def test_params_supported_scope():
+    L = rb.lib()
+    mk = lambda s, f, c: C.byref(rb._ParamsC(s, f, c))
+    assert L.redux_params_supported(mk(8, 14, 16)) == rb.OK
+    assert L.redux_params_supported(mk(8, 30, 34)) == rb.OK
+    assert L.redux_params_supported(mk(4, 10, 16)) == rb.UNSUPPORTED
+    assert L.redux_params_supported(mk(12, 14, 16)) == rb.UNSUPPORTED
+    assert L.redux_params_supported(mk(8, 9, 16)) == rb.INVALID_INPUT
+
+
+def test_compress_bound():
+    assert rb.compress_bound(0, 16) == 2 and rb.compress_bound(0, 32) == 4
+    assert rb.compress_bound(65536, 16) == (65537 * 16 + 7) // 8
+
+
+def _magic(d, nbits, wide):
+    m, sh = C.c_uint64(), C.c_uint32()
+    assert rb.lib().redux_debug_magic(d, nbits, wide, C.byref(m), C.byref(sh)) == rb.OK
+    return m.value, sh.value
+
+
+@pytest.mark.parametrize("nbits,wide", [(22, 0), (26, 0), (30, 0), (34, 1), (46, 1), (54, 1), (62, 1)])
+def test_count_reciprocal_is_exact(nbits, wide):
+    """floor(n/d) == mulhi(n, magic) >> shift for every count d the coder can see and adversarial n."""
+    rng = np.random.default_rng(nbits)
+    L = rb.lib()
+    fmax_bits = min(30, nbits - 12)
+    ds = [257, 258, 259, 511, 512, 513, 1023, 1024, 1025, 4095, 4096, 16383, 65535, 65536, 65537,
+          (1 << fmax_bits) - 1, (1 << fmax_bits) - 2]
+    ds += [int(x) for x in rng.integers(257, 1 << fmax_bits, size=60)]
+    top = (1 << nbits) - 1
+    for d in ds:
+        if d >= (1 << fmax_bits):
+            continue
+        m, sh = _magic(d, nbits, wide)
+        assert m < (1 << (64 if wide else 32))
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, top, top - 1, (top // d) * d, (top // d) * d - 1]
+        ns += [int(x) for x in rng.integers(0, top, size=200, dtype=np.uint64)]
+        ks = [int(x) for x in rng.integers(1, max(2, top // d), size=100, dtype=np.uint64)]
+        ns += [k * d - 1 for k in ks] + [k * d for k in ks]
+        for n in ns:
+            n = int(n)
+            if 0 <= n <= top:
+                assert L.redux_debug_magic_divide(n, m, sh, wide) == n // d, (n, d, nbits)
+
+
+def test_count_reciprocal_exhaustive_small():
+    """All numerators for a small class: nbits=18 over d in [257, 1023]."""
+    for d in range(257, 1024, 7):
+        m, sh = _magic(d, 18, 0)
+        n = np.arange(0, 1 << 18, dtype=np.uint64)
+        got = ((n * np.uint64(m)) >> np.uint64(32)) >> np.uint64(sh)
+        assert (got == n // np.uint64(d)).all(), d
+
+
+def _renorm_loop(low, high, c):
+    """The reference's renormalisation loop, src/codec.rs:62-89 (bits ignored)."""
+    q, half, q3, mx = 1 << (c - 2), 2 << (c - 2), 3 << (c - 2), (1 << c) - 1
+    n1 = k = 0
+    order = []
+    while True:
+        if high < half or low >= half:
+            n1 += 1
+            order.append("e12")
+        elif low >= q and high < q3:
+            k += 1
+            low -= q
+            high -= q
+            order.append("e3")
+        else:
+            break
+        high = ((high << 1) + 1) & mx
+        low = (low << 1) & mx
+    return n1, k, low, high, order
+
+
+@pytest.mark.parametrize("c", [12, 16, 18, 24, 30, 32, 34, 44, 61])
+def test_renorm_closed_form_equals_loop(c):
+    """the loop is n1 E1/E2 steps followed by k E3 steps, never interleaved.
+    (A degenerate interval low == high is reachable in the coder and renormalises to the full range.)"""
+    rng = np.random.default_rng(c)
+    L = rb.lib()
+    mx = (1 << c) - 1
+    cases = [(0, mx), ((1 << (c - 1)) - 1, 1 << (c - 1)), (1 << (c - 2), (3 << (c - 2)) - 1),
+             ((1 << (c - 1)) - 2, (1 << (c - 1)) + 1), (mx - 1, mx), (0, 1)]
+    for _ in range(3000):
+        a, b = sorted(int(x) for x in rng.integers(0, mx, size=2, dtype=np.uint64, endpoint=True))
+        cases.append((a, b))
+        w = int(rng.integers(1, c))          # narrow intervals: many common bits
+        base = int(rng.integers(0, mx - (1 << w) + 1, dtype=np.uint64)) if mx > (1 << w) else 0
+        a2 = base + int(rng.integers(0, 1 << w, dtype=np.uint64))
+        b2 = base + int(rng.integers(0, 1 << w, dtype=np.uint64))
+        cases.append((min(a2, b2), max(a2, b2)))
+        mid = 1 << (c - 1)                   # straddling the middle: E3 runs
+        d1 = int(rng.integers(1, 1 << w, dtype=np.uint64)) if w > 0 else 1
+        d2 = int(rng.integers(0, 1 << w, dtype=np.uint64))
+        if mid - d1 >= 0 and mid + d2 <= mx:
+            cases.append((mid - d1, mid + d2))
+    for low, high in cases:
+        n1, k, nl, nh = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+        L.redux_debug_renorm(low, high, c, C.byref(n1), C.byref(k), C.byref(nl), C.byref(nh))
+        if low == high:
+            # the loop never terminates on paper for low == high only in the sense that every step is
+            # E1/E2: after c steps the registers are (0, max); the reference stops there because the
+            # interval is then the full range.
+            assert (n1.value, k.value, nl.value, nh.value) == (c, 0, 0, mx)
+            continue
+        e = _renorm_loop(low, high, c)
+        assert (n1.value, k.value, nl.value, nh.value) == e[:4], (low, high, c)
+        assert e[4] == ["e12"] * e[0] + ["e3"] * e[1]
+
+
+def test_generator_host_is_deterministic_and_mixed():
+    a = rb.generate_blocks_host(0, 8, 4096, 0x5EED202610180000)
+    b = rb.generate_blocks_host(0, 8, 4096, 0x5EED202610180000)
+    assert (a == b).all()
+    c = rb.generate_blocks_host(4, 4, 4096, 0x5EED202610180000)
+    assert (a[4 * 4096:] == c).all(), "blocks depend on the absolute block index only"
+    ent = []
+    for i in range(4):
+        blk = a[i * 4096:(i + 1) * 4096]
+        p = np.bincount(blk, minlength=256) / blk.size
+        p = p[p > 0]
+        ent.append(float(-(p * np.log2(p)).sum()))
+    assert ent[0] > 7.8 and 4.0 < ent[1] < 5.2 and 1.6 < ent[2] < 2.3 and ent[3] < 0.5, ent
+
+
+def test_no_gpu_means_cuda_error_not_fallback():
+    """The product path must fail loudly without a device (no CPU fallback)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(rb.CudaError):
+        rb.Context()
+    import io
+    with pytest.raises(rb.CudaError):
+        rb.compress(io.BytesIO(b"redux"), io.BytesIO(), rb.AdaptiveTreeModel(rb.Parameters(8, 14, 16)))
+
+
+def test_product_package_does_not_touch_oracle():
+    """Only tests/, smoke() and bench.py's CPU legs may use oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "redux_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "redux_oracle" not in text and "oracle_lib" not in text, os.path.join(dirpath, f)

@@ -1,0 +1,276 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Needs a B200: `pytest -m gpu`.
+Bit-exact is the bar: every compressed byte, every decoded byte, every count and status."""
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as o
+import redux_b200 as rb
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SEED = 0x5EED202610180000
+TRIPLES = [(8, 14, 16), (8, 22, 24), (8, 30, 32)]          # tests/corpora.rs:35 (bits, bits+2)
+KINDS = [(rb.AdaptiveLinearModel, o.LINEAR), (rb.AdaptiveTreeModel, o.TREE)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = rb.Context()
+    yield c
+    c.close()
+
+
+def concat(blocks):
+    lens = np.array([len(b) for b in blocks], dtype=np.uint64)
+    off = np.zeros(len(blocks) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    data = np.frombuffer(b"".join(blocks), dtype=np.uint8) if off[-1] else np.zeros(0, dtype=np.uint8)
+    return data, off
+
+
+def oracle_encode_all(blocks, kind, params):
+    outs = []
+    for b in blocks:
+        rc, out, ic, oc = o.compress(b, kind, params)
+        assert rc == o.OK and ic == len(b)
+        outs.append(out)
+    return outs
+
+
+def check_encode(ctx, blocks, model_cls, okind, params, expect=None):
+    model = model_cls(rb.Parameters(*params))
+    data, off = concat(blocks)
+    out, out_off, status = ctx.encode_batch(data, off, model)
+    assert (status == 0).all(), status[status != 0][:8]
+    expect = expect if expect is not None else oracle_encode_all(blocks, okind, params)
+    for i, e in enumerate(expect):
+        got = out[int(out_off[i]):int(out_off[i + 1])].tobytes()
+        if got != e:
+            n = min(len(got), len(e))
+            first = next((j for j in range(n) if got[j] != e[j]), n)
+            raise AssertionError("block %d (len %d) params %s: sizes %d vs oracle %d, first diff at byte %d: %s vs %s"
+                                 % (i, len(blocks[i]), params, len(got), len(e), first,
+                                    got[first:first + 8].hex(), e[first:first + 8].hex()))
+    return out, out_off, expect
+
+
+def check_decode(ctx, comp, comp_off, blocks, model_cls, params, slack=0):
+    model = model_cls(rb.Parameters(*params))
+    lens = np.array([len(b) + slack for b in blocks], dtype=np.uint64)
+    raw_off = np.zeros(len(blocks) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=raw_off[1:])
+    raw, raw_lens, consumed, status = ctx.decode_batch(comp, comp_off, raw_off, model)
+    assert (status == 0).all(), status[status != 0][:8]
+    for i, b in enumerate(blocks):
+        assert int(raw_lens[i]) == len(b), (i, int(raw_lens[i]), len(b))
+        assert int(consumed[i]) == int(comp_off[i + 1] - comp_off[i]), "decoder must consume the whole stream"
+        got = raw[int(raw_off[i]):int(raw_off[i]) + len(b)].tobytes()
+        if got != b:
+            first = next(j for j in range(len(b)) if got[j] != b[j])
+            raise AssertionError("decode block %d params %s: first diff at %d" % (i, params, first))
+
+
+def test_kat_vectors_single_stream(ctx):
+    """Golden vectors (SURVEY B.1 + second reading) through redux_compress / redux_decompress."""
+    vecs = [v for v in json.load(open(os.path.join(GOLD, "kat_vectors.json"))) if v["params"][0] == 8]
+    assert len(vecs) >= 80
+    for v in vecs:
+        p = tuple(v["params"])
+        data, want = bytes.fromhex(v["input"]), bytes.fromhex(v["compressed"])
+        for cls, _ in KINDS:
+            model = cls(rb.Parameters(*p))
+            out, (ic, oc) = ctx.compress(data, model)
+            assert out == want, (v["name"], p, out.hex()[:32], want.hex()[:32])
+            assert (ic, oc) == (len(data), len(want))
+            dec, (ic2, oc2) = ctx.decompress(out, cls(rb.Parameters(*p)), len(data) + 8)
+            assert dec == data and (ic2, oc2) == (len(want), len(data))
+
+
+def test_dropin_compress_decompress_doctest():
+    """The doctest of src/lib.rs:23-39 through the Python mirror of the crate API."""
+    data = bytes([0x72, 0x65, 0x64, 0x75, 0x78])
+    compressed = io.BytesIO()
+    counts = rb.compress(io.BytesIO(data), compressed, rb.AdaptiveTreeModel.new(rb.Parameters.new(8, 14, 16)))
+    assert counts == (5, 7) and compressed.getvalue().hex() == "71f23484c4c510"
+    decompressed = io.BytesIO()
+    counts = rb.decompress(io.BytesIO(compressed.getvalue()), decompressed,
+                           rb.AdaptiveTreeModel.new(rb.Parameters.new(8, 14, 16)))
+    assert counts == (7, 5) and decompressed.getvalue() == data
+
+
+def test_empty_and_tiny_blocks(ctx):
+    blocks = [b"", b"a", b"", b"ab", b"\x00", b"\xff" * 3, b""] + [bytes([i]) * i for i in range(1, 40)]
+    for params in TRIPLES:
+        for cls, ok in KINDS:
+            out, out_off, _ = check_encode(ctx, blocks, cls, ok, params)
+            check_decode(ctx, out, out_off, blocks, cls, params)
+
+
+@pytest.mark.parametrize("params", TRIPLES + [(8, 10, 12), (8, 10, 16), (8, 12, 18), (8, 16, 18), (8, 20, 22),
+                                              (8, 24, 30), (8, 17, 32), (8, 30, 34), (8, 20, 44), (8, 10, 54)])
+def test_ragged_mixed_entropy_batch(ctx, params):
+    """Ragged lengths (0..5000), every generator class, both model kinds; freeze regime for small f."""
+    rng = np.random.default_rng(params[1] * 100 + params[2])
+    n = 300
+    lens = rng.integers(0, 5000, size=n)
+    lens[:8] = [0, 1, 2, 3, 15, 16, 17, 4999]
+    base = rb.generate_blocks_host(0, n, 5000, SEED)
+    blocks = [base[i * 5000:i * 5000 + int(lens[i])].tobytes() for i in range(n)]
+    for cls, ok in KINDS[1:] if params not in TRIPLES else KINDS:
+        out, out_off, _ = check_encode(ctx, blocks, cls, ok, params)
+        check_decode(ctx, out, out_off, blocks, cls, params)
+
+
+def test_full_size_blocks_64k(ctx):
+    """The headline shape: 64 KiB blocks (u16 table, last update may wrap node counters)."""
+    n = 96
+    base = rb.generate_blocks_host(0, n, 65536, SEED)
+    blocks = [base[i * 65536:(i + 1) * 65536].tobytes() for i in range(n)]
+    blocks[5] = b"\x41" * 65536            # every update lands on one path: increments reach 65535/65536
+    blocks[6] = bytes([0x7f]) * 65536
+    for params in TRIPLES:
+        out, out_off, _ = check_encode(ctx, blocks, rb.AdaptiveTreeModel, o.TREE, params)
+        check_decode(ctx, out, out_off, blocks, rb.AdaptiveTreeModel, params)
+
+
+def test_long_blocks_need_wide_table(ctx):
+    """Blocks longer than 65,536 symbols with a late freeze use the 32-bit table."""
+    n = 6
+    L = 200000
+    base = rb.generate_blocks_host(100, n, L, SEED)
+    blocks = [base[i * L:(i + 1) * L].tobytes() for i in range(n)]
+    blocks.append(b"\x00" * 150000)
+    for params in [(8, 30, 32), (8, 20, 22), (8, 16, 18), (8, 14, 16)]:
+        out, out_off, _ = check_encode(ctx, blocks, rb.AdaptiveTreeModel, o.TREE, params)
+        check_decode(ctx, out, out_off, blocks, rb.AdaptiveTreeModel, params)
+
+
+def test_unaligned_offsets_and_slack(ctx):
+    """Blocks start at arbitrary byte offsets in both directions; raw slots have spare capacity."""
+    rng = np.random.default_rng(5)
+    blocks = [rng.integers(0, 256, size=int(k), dtype=np.uint8).tobytes() for k in rng.integers(1, 300, size=200)]
+    out, out_off, _ = check_encode(ctx, blocks, rb.AdaptiveTreeModel, o.TREE, (8, 22, 24))
+    check_decode(ctx, out, out_off, blocks, rb.AdaptiveTreeModel, (8, 22, 24), slack=0)
+    check_decode(ctx, out, out_off, blocks, rb.AdaptiveTreeModel, (8, 22, 24), slack=3)
+
+
+def test_truncated_and_garbage_streams(ctx):
+    """Error behaviour of decompress(): Eof on truncation with the decoded prefix kept
+    (src/bitio/mod.rs:106-108 via src/codec.rs:50), trailing garbage not read."""
+    params = (8, 22, 24)
+    model = rb.AdaptiveTreeModel(rb.Parameters(*params))
+    data = rb.generate_blocks_host(1, 1, 3000, SEED).tobytes()
+    rc, comp, _, _ = o.compress(data, o.TREE, params)
+    streams, expect = [], []
+    for cut in (0, 1, 2, 3, 4, 5, len(comp) // 3, len(comp) // 2, len(comp) - 2, len(comp) - 1):
+        streams.append(comp[:cut])
+        expect.append(o.decompress(comp[:cut], o.TREE, params, out_cap=4000))
+    streams.append(comp + b"\xde\xad\xbe\xef\x00\x11")
+    expect.append(o.decompress(streams[-1], o.TREE, params, out_cap=4000))
+    cdata, coff = concat(streams)
+    raw_off = np.arange(len(streams) + 1, dtype=np.uint64) * np.uint64(4000)
+    raw, raw_lens, consumed, status = ctx.decode_batch(cdata, coff, raw_off, model, check=False)
+    for i, (erc, edec, eic, eoc) in enumerate(expect):
+        assert int(status[i]) == erc, (i, int(status[i]), erc)
+        assert int(raw_lens[i]) == eoc and int(consumed[i]) == eic, (i, int(raw_lens[i]), eoc, int(consumed[i]), eic)
+        assert raw[i * 4000:i * 4000 + eoc].tobytes() == edec
+    assert int(status[-1]) == 0 and int(consumed[-1]) == len(comp)
+    with pytest.raises(rb.Eof):
+        ctx.decompress(comp[: len(comp) // 2], model, 4000)
+    with pytest.raises(rb.Eof):
+        rb.decompress(io.BytesIO(b""), io.BytesIO(), rb.AdaptiveTreeModel(rb.Parameters(8, 14, 16)))
+
+
+def test_random_garbage_never_faults(ctx):
+    """Arbitrary bytes are a valid (if meaningless) code stream: the decoder must agree with the oracle
+    on status, lengths and bytes, and stop at the slot capacity."""
+    rng = np.random.default_rng(11)
+    params = (8, 14, 16)
+    model = rb.AdaptiveTreeModel(rb.Parameters(*params))
+    streams = [rng.integers(0, 256, size=int(k), dtype=np.uint8).tobytes() for k in rng.integers(0, 400, size=64)]
+    cdata, coff = concat(streams)
+    cap = 2048
+    raw_off = np.arange(len(streams) + 1, dtype=np.uint64) * np.uint64(cap)
+    raw, raw_lens, consumed, status = ctx.decode_batch(cdata, coff, raw_off, model, check=False)
+    for i, s in enumerate(streams):
+        erc, edec, eic, eoc = o.decompress(s, o.TREE, params, out_cap=cap)
+        if erc == o.IO_ERROR:      # oracle sink full <-> device OUT_CAPACITY
+            assert int(status[i]) == rb.OUT_CAPACITY and int(raw_lens[i]) == cap
+            assert raw[i * cap:(i + 1) * cap].tobytes() == edec
+        else:
+            assert int(status[i]) == erc and int(raw_lens[i]) == eoc and int(consumed[i]) == eic
+            assert raw[i * cap:i * cap + eoc].tobytes() == edec
+
+
+def test_output_capacity_is_reported(ctx):
+    blocks = [rb.generate_blocks_host(0, 1, 4096, SEED).tobytes()] * 4
+    data, off = concat(blocks)
+    model = rb.AdaptiveTreeModel(rb.Parameters(8, 14, 16))
+    small = np.zeros(5000, dtype=np.uint8)
+    with pytest.raises(rb.OutCapacity):
+        ctx.encode_batch(data, off, model, out=small)
+    out, out_off, status = ctx.encode_batch(data, off, model, out=small, check=False)
+    assert int(status[0]) == 0 and rb.OUT_CAPACITY in [int(s) for s in status]
+
+
+def test_invalid_and_unsupported_parameters(ctx):
+    with pytest.raises(rb.InvalidInput):
+        rb.Parameters(8, 9, 16)
+    data, off = concat([b"abc"])
+    model = rb.AdaptiveTreeModel(rb.Parameters(4, 10, 16))
+    with pytest.raises(rb.Unsupported):
+        ctx.encode_batch(data, off, model)
+
+
+def test_generator_device_equals_host(ctx):
+    import torch
+    n, L = 64, 4099
+    d = torch.empty(n * L, dtype=torch.uint8, device="cuda")
+    ctx.generate_blocks_device(d, 7, n, L, SEED, device=torch.cuda.current_device(),
+                               stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (d.cpu().numpy() == rb.generate_blocks_host(7, n, L, SEED)).all()
+
+
+def test_device_resident_batch_roundtrip_and_sampled_parity(ctx):
+    """Device-resident API at a multi-wave size: 8,192 blocks x 64 KiB generated on the GPU, encoded and
+    decoded without leaving HBM; a sample of blocks is memcmp'd with the oracle and the whole batch must
+    round-trip (size-independent property)."""
+    import torch
+    dev = torch.cuda.current_device()
+    st = torch.cuda.current_stream().cuda_stream
+    n, L = 8192, 65536
+    params = (8, 14, 16)
+    model = rb.AdaptiveTreeModel(rb.Parameters(*params))
+    raw = torch.empty(n * L, dtype=torch.uint8, device="cuda")
+    ctx.generate_blocks_device(raw, 0, n, L, SEED, device=dev, stream=st)
+    in_off = torch.arange(n + 1, dtype=torch.int64, device="cuda") * L
+    cap = n * (L + L // 8)
+    comp = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    comp_off = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    status = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    ctx.encode_batch_device(raw, in_off, n, L, comp, cap, comp_off, status, model, device=dev, stream=st)
+    torch.cuda.synchronize()
+    assert int(status.abs().max()) == 0
+    offs = comp_off.cpu().numpy().astype(np.uint64)
+    assert int(offs[-1]) <= cap
+    sample = [0, 1, 2, 3, 4097, 8191]
+    host_raw = raw.cpu().numpy()
+    host_comp = comp[: int(offs[-1])].cpu().numpy()
+    for i in sample:
+        rc, e, _, _ = o.compress(host_raw[i * L:(i + 1) * L], o.TREE, params)
+        assert host_comp[int(offs[i]):int(offs[i + 1])].tobytes() == e, i
+    back = torch.zeros(n * L, dtype=torch.uint8, device="cuda")
+    raw_lens = torch.zeros(n, dtype=torch.int64, device="cuda")
+    consumed = torch.zeros(n, dtype=torch.int64, device="cuda")
+    status.fill_(-1)
+    ctx.decode_batch_device(comp, comp_off, n, L, back, in_off, raw_lens, consumed, status, model, device=dev, stream=st)
+    torch.cuda.synchronize()
+    assert int(status.abs().max()) == 0
+    assert bool((raw_lens == L).all())
+    assert bool((consumed == (comp_off[1:] - comp_off[:-1])).all())
+    assert torch.equal(back, raw)
