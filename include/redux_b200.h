@@ -128,7 +128,7 @@ int redux_decode_batch(redux_ctx_t *ctx, int model_kind, const redux_params_t *p
 
 /* ---- batch, device-resident buffers (kernel-only timing; all pointers are device memory on
  * `device`, which must be one of the context's devices; work is enqueued on `stream` (a
- * cudaStream_t, NULL = the context's own stream for that device) and is asynchronous).
+ * cudaStream_t; NULL = the CUDA default stream) and is asynchronous).
  * max_block_len: an upper bound of every block's raw length (sizes the per-block output slots).
  * total_in_bytes = in_offsets[n_blocks] as known by the host. */
 int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *stream, int model_kind,
@@ -143,7 +143,7 @@ int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *stream, int mo
                               uint64_t max_block_len,
                               uint8_t *d_raw, const uint64_t *d_raw_offsets, uint64_t *d_raw_lens,
                               uint64_t *d_consumed, int32_t *d_status);
-/* Waits for the work enqueued on `stream` (or the context's stream) of `device`. */
+/* Waits for the work enqueued on `stream` of `device`. */
 int redux_ctx_synchronize(redux_ctx_t *ctx, int device, void *stream);
 
 /* ---- synthetic workload (BASELINE.json configs 3-4; DESIGN.md "generator"): fills

@@ -378,7 +378,7 @@ extern "C" int redux_ctx_synchronize(redux_ctx_t *ctx, int device, void *stream)
     DeviceState *d = find_dev(ctx, device);
     if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
     DeviceGuard g(device);
-    CU_TRY(ctx, cudaStreamSynchronize(stream ? (cudaStream_t)stream : d->stream));
+    CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
     return REDUX_OK;
 }
 
@@ -400,7 +400,7 @@ extern "C" int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *str
     if (!d_in_offsets || !d_out_offsets || !d_status || (!d_out && out_capacity))
         return fail(ctx, REDUX_INVALID_INPUT, "NULL buffer");
     DeviceGuard g(device);
-    cudaStream_t s = stream_ ? (cudaStream_t)stream_ : d->stream;
+    cudaStream_t s = (cudaStream_t)stream_;   // NULL = the default stream, as in CUDA
     if (n_blocks == 0) { CU_TRY(ctx, cudaMemsetAsync(d_out_offsets, 0, sizeof(uint64_t), s)); return REDUX_OK; }
     if (n_blocks > 0x7FFFFFFFull * 32) return fail(ctx, REDUX_UNSUPPORTED, "too many blocks in one launch");
 
@@ -461,7 +461,7 @@ extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *str
     if (!d_comp_offsets || !d_raw_offsets || !d_raw_lens || !d_consumed || !d_status)
         return fail(ctx, REDUX_INVALID_INPUT, "NULL buffer");
     DeviceGuard g(device);
-    cudaStream_t s = stream_ ? (cudaStream_t)stream_ : d->stream;
+    cudaStream_t s = (cudaStream_t)stream_;   // NULL = the default stream, as in CUDA
     const void *magic = nullptr;
     if ((rc = get_magic(ctx, d, s, pl, &magic))) return rc;
 
@@ -490,7 +490,7 @@ extern "C" int redux_generate_blocks_device(redux_ctx_t *ctx, int device, void *
     if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
     if (n_blocks == 0 || block_len == 0) return REDUX_OK;
     DeviceGuard g(device);
-    cudaStream_t s = stream_ ? (cudaStream_t)stream_ : d->stream;
+    cudaStream_t s = (cudaStream_t)stream_;   // NULL = the default stream, as in CUDA
     {
         KernelTimer kt(ctx, device, s, REDUX_KERNEL_GENERATE);
         generate_kernel<<<148 * 8, 256, 0, s>>>(d_out, first_block, n_blocks, block_len, seed, d->text_lut);
