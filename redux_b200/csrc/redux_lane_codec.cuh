@@ -2,19 +2,28 @@
 //
 // What the reference does per stream on one CPU thread (src/codec.rs:55-176 over
 // src/model/adaptive_tree.rs) runs here in every lane of every warp:
-//   * the stream's Fenwick table lives in shared memory, LANE-INTERLEAVED: node i of lane l is word
-//     tab[i*32 + l], so any 32 lanes touching any 32 nodes hit 32 different banks -- the
-//     data-dependent walks are bank-conflict free by construction;
+//   * the stream's Fenwick table lives in shared memory, LANE-INTERLEAVED so that lane l only ever
+//     touches bank l: whatever nodes the 32 data-dependent walks visit, an access is one wavefront.
+//     32-bit tables: node i of lane l is word i*32 + l.  16-bit tables: the word (i>>1)*32 + l holds
+//     node i (even, low half) and node i+1 (odd, high half) of lane l;
 //   * the table stores INCREMENTS only.  The reference initialises tree[i] = lowbit(i)
 //     (adaptive_tree.rs:43-45) and a Fenwick prefix path decomposes i into its set bits, so
 //     cum(i) = i + sum(increments on the path).  Node 256 (every data symbol's update ends there,
 //     adaptive_tree.rs:86-89) equals the number of updates so far and node 257 (EOF) is constant 1:
-//     neither is stored.  256 x u16 per stream = 512 B -> 14 warps (448 streams) per SM;
+//     neither is stored.  256 x u16 per stream = 512 B -> 14 warps (448 streams) per SM, which is
+//     what lets 65,536 blocks be resident on 148 SMs in ONE wave (443 streams per SM);
+//   * walks are flattened: the nodes of a prefix path are s & (0xFF << b) for the set bits b of s and
+//     the nodes of an update path are (s | (2^k - 1)) + 1 for the clear bits k-1 of s, so every load
+//     address is independent of every other load (no pointer chasing) and absent nodes read the
+//     always-zero node 0 instead of branching;
 //   * count_t = min(257 + t, FMAX) depends on the position only, so the two divisions
-//     by count (src/codec.rs:59-60) are multiplications by a per-position magic shared by all streams;
+//     by count (src/codec.rs:59-60) are multiplications by a per-position magic shared by all streams,
+//     and the loop splits into an adaptive phase (t < FMAX-257) and a frozen phase (no updates,
+//     constant reciprocal);
 //   * renormalisation (src/codec.rs:62-89 / :140-158) is the closed form of redux_common.cuh;
 //   * bits are packed into a 64-bit register and leave as whole big-endian 32-bit words
-//     (MSB-first bytes, src/bitio/mod.rs:148-198) into the stream's private output slot.
+//     (MSB-first bytes, src/bitio/mod.rs:148-198) into the stream's private output slot; raw bytes
+//     arrive as 16-byte vector loads prefetched one chunk ahead.
 // No __syncthreads, no warp collectives: lanes are fully independent and may be ragged.
 #pragma once
 #include "redux_common.cuh"
@@ -23,7 +32,7 @@ namespace rdx {
 
 constexpr int kLaneWarpsPerCta = 7;                 // 7 warps x 16 KiB tables; 2 CTAs per SM
 constexpr int kLaneThreads = kLaneWarpsPerCta * 32;
-constexpr int kTabNodes = 256;                      // nodes 0..255 (node 0 is never touched)
+constexpr int kTabNodes = 256;                      // nodes 0..255 (node 0 stays 0: the "absent" node)
 
 struct LaneEncJob {
     const uint8_t *in;          // raw bytes
@@ -79,44 +88,63 @@ template <> struct Cls<kHuge> {
 };
 
 // ------------------------------------------------------------------ Fenwick increments in smem
+// Indices below are in units of TW from the lane's base pointer.  A node row is 32 entries apart
+// ("<< 5"); in the 16-bit layout an odd node n shares the word of even node n-1, i.e. sits at
+// (n-1)*32 + 1 = n*32 - 31.
 template <typename TW>
 struct LaneTable {
-    TW *t;   // already offset by lane: node i at t[i*32]
-    __device__ __forceinline__ uint32_t ld(uint32_t node) const { return t[node * 32]; }
+    static constexpr int kOddAdj = (sizeof(TW) == 2) ? -31 : 0;
+    static constexpr int kLaneMul = (sizeof(TW) == 2) ? 2 : 1;
+    TW *t;   // table base of the warp + lane * kLaneMul
 
+    __device__ __forceinline__ void init(void *smem, uint32_t warp, uint32_t lane) {
+        t = reinterpret_cast<TW *>(smem) + (size_t)warp * kTabNodes * 32 + lane * kLaneMul;
+    }
     __device__ __forceinline__ void clear() {
+        // every word of the lane's column: 256 (u32) or 128 (u16 pairs) 32-bit words
+        uint32_t *w = reinterpret_cast<uint32_t *>(t);
+        constexpr int kWords = kTabNodes * (int)sizeof(TW) / 4;
 #pragma unroll 8
-        for (int i = 0; i < kTabNodes; ++i) t[i * 32] = 0;
+        for (int i = 0; i < kWords; ++i) w[i * 32] = 0;
     }
 
     // (cum(s), cum(s+1)) for a data symbol s in 0..255: the paired walk of adaptive_tree.rs:63-80
     // flattened.  Bits of s below its lowest zero bit belong to cum(s) only, bits above to both,
     // node s+1 to cum(s+1) only.  `updates` = increments of the unstored node 256.
     __device__ __forceinline__ void query(uint32_t s, uint32_t updates, uint32_t &cl, uint32_t &ch) const {
-        const uint32_t lowmask = s & ~(s + 1);
-        uint32_t only_l = 0, both = 0;
+        const uint32_t S = s << 5;
+        const uint32_t lowmask = s & ~(s + 1);                  // trailing ones of s
+        const uint32_t odd = s & 1u;
+        // b = 0: node s itself when s is odd (an odd node); belongs to cum(s) only
+        uint32_t total = t[odd ? (int)S + kOddAdj : 0];
+        uint32_t both = 0;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
+        for (int b = 1; b < 8; ++b) {
             const uint32_t bit = 1u << b;
-            if (s & bit) {
-                uint32_t v = ld(s & (0xFFu << b));
-                if (lowmask & bit) only_l += v; else both += v;
-            }
+            const uint32_t v = t[(s & bit) ? (S & (0x1FE0u << b)) : 0u];   // even node s & (0xFF<<b)
+            total += v;
+            both += (lowmask & bit) ? 0u : v;
         }
-        const uint32_t top = (s == 255u) ? updates : ld(s + 1);
-        cl = s + only_l + both;
-        ch = s + 1 + top + both;
+        // node s+1: odd when s is even; node 256 is not stored
+        const uint32_t it = (s == 255u) ? 0u : (odd ? S + 32u : (uint32_t)((int)S + 32 + kOddAdj));
+        const uint32_t top = t[it] + ((s == 255u) ? updates : 0u);
+        cl = s + total;
+        ch = s + 1u + top + both;
     }
 
-    // update(s+1) of adaptive_tree.rs:83-92 minus the two unstored nodes.
+    // update(s+1) of adaptive_tree.rs:83-92 minus the two unstored nodes: node s+1, then for every
+    // clear bit k-1 of s the node (s | (2^k-1)) + 1, while below 256.
     __device__ __forceinline__ void update(uint32_t s) {
-        uint32_t i = s + 1;
+        const uint32_t S = s << 5;
+        if (s != 255u) {
+            const uint32_t i0 = (s & 1u) ? S + 32u : (uint32_t)((int)S + 32 + kOddAdj);
+            t[i0] = (TW)(t[i0] + 1);
+        }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (i < 256u) {
-                t[i * 32] = (TW)(t[i * 32] + 1);
-                i += i & (0u - i);
-            }
+        for (int k = 1; k < 8; ++k) {
+            const uint32_t base = S | (((1u << k) - 1u) << 5);           // (s | mask_k) * 32
+            if (!(s & (1u << (k - 1))) && base < (255u << 5))
+                t[base + 32u] = (TW)(t[base + 32u] + 1);
         }
     }
 };
@@ -126,49 +154,115 @@ struct BitSink {
     uint64_t acc;      // newest bit at bit 0
     uint32_t nb;       // valid bits in acc, < 32 between calls
     uint32_t *w;       // next output word (slot is 16-byte aligned)
-    uint32_t nwords;
+    uint32_t *w0;
 
-    __device__ __forceinline__ void init(uint8_t *slot) { acc = 0; nb = 0; w = (uint32_t *)slot; nwords = 0; }
-    // append the low n (<= 32) bits of v (v < 2^n)
+    __device__ __forceinline__ void init(uint8_t *slot) { acc = 0; nb = 0; w = w0 = (uint32_t *)slot; }
+    // append the low n (0..32) bits of v (v < 2^n)
     __device__ __forceinline__ void put(uint32_t v, uint32_t n) {
         acc = (acc << n) | v;
         nb += n;
         if (nb >= 32) {
-            uint32_t word = (uint32_t)(acc >> (nb - 32));
-            w[nwords++] = __byte_perm(word, 0, 0x0123);   // big-endian: first bit -> MSB of first byte
             nb -= 32;
+            *w++ = __byte_perm((uint32_t)(acc >> nb), 0, 0x0123);   // first bit -> MSB of first byte
         }
     }
-    // `bits` = n >= 1 code bits (MSB first); the first is followed by `pend` copies of its inverse
-    // (put_bit, src/codec.rs:39-46).
-    __device__ __forceinline__ void put_with_pending(uint32_t bits, uint32_t n, uint32_t pend) {
-        const uint32_t b = (bits >> (n - 1)) & 1u;
-        const uint32_t rest = bits & ((1u << (n - 1)) - 1u);
-        if (n + pend <= 32) {
-            // [b][pend x !b][rest]
-            uint32_t run = b ? 0u : ((1u << pend) - 1u);               // pend <= 31 here
-            uint32_t v = ((((b << pend) | run)) << (n - 1)) | rest;
-            put(v, n + pend);
+    // x = n1 >= 1 code bits (MSB first); the first is followed by `pend` copies of its inverse
+    // (put_bit, src/codec.rs:39-46).  With b = first bit: [b][pend x !b][rest] as one number is
+    // x + 2^(n1+pend-1) - 2^(n1-1) for either value of b.
+    __device__ __forceinline__ void put_code(uint64_t x, uint32_t n1, uint32_t pend) {
+        const uint32_t n = n1 + pend;
+        if (n <= 32) {
+            put((uint32_t)x + (1u << (n - 1)) - (1u << (n1 - 1)), n);
         } else {
+            const uint32_t b = (uint32_t)(x >> (n1 - 1)) & 1u;
             put(b, 1);
             while (pend > 0) {
-                uint32_t m = pend < 32 ? pend : 32;
-                put(b ? 0u : (m == 32 ? 0xFFFFFFFFu : ((1u << m) - 1u)), m);
+                const uint32_t m = pend < 32 ? pend : 32;
+                put(b ? 0u : (0xFFFFFFFFu >> (32 - m)), m);
                 pend -= m;
             }
-            if (n > 1) put(rest, n - 1);
+            uint32_t r = n1 - 1;                               // remaining bits of x
+            if (r > 32) { put((uint32_t)(x >> 32) & (0xFFFFFFFFu >> (64 - r)), r - 32); r = 32; }
+            if (r) put((uint32_t)x & (0xFFFFFFFFu >> (32 - r)), r);
         }
     }
     // flush_bits (src/bitio/mod.rs:183-198): left-align, zero-pad. Returns the byte count.
     __device__ __forceinline__ uint32_t finish() {
-        uint32_t bytes = nwords * 4 + (nb + 7) / 8;
-        if (nb) {
-            uint32_t word = (uint32_t)(acc << (32 - nb));
-            w[nwords] = __byte_perm(word, 0, 0x0123);
-        }
+        const uint32_t bytes = (uint32_t)(w - w0) * 4 + (nb + 7) / 8;
+        if (nb) *w = __byte_perm((uint32_t)(acc << (32 - nb)), 0, 0x0123);
         return bytes;
     }
 };
+
+// ------------------------------------------------------------------ byte source (encoder input)
+// 16-byte aligned vector loads, one chunk prefetched ahead; bytes are shifted out of a word register.
+struct ByteSource {
+    const uint4 *p;         // next chunk to prefetch
+    const uint4 *last;      // last chunk that may be read
+    uint4 nxt;              // prefetched chunk
+    uint32_t w, x, y, z;    // current word (already shifted) and the following words of the chunk
+    uint32_t pos;           // byte position (chunk-relative phase in the low 4 bits)
+
+    __device__ __forceinline__ void init(const uint8_t *src, uint32_t len) {
+        const uintptr_t a = (uintptr_t)src;
+        const uint4 *c0 = reinterpret_cast<const uint4 *>(a & ~(uintptr_t)15);
+        pos = (uint32_t)(a & 15);
+        last = reinterpret_cast<const uint4 *>((a + (len ? len - 1 : 0)) & ~(uintptr_t)15);
+        uint4 q = make_uint4(0, 0, 0, 0);
+        nxt = q;
+        if (len) {
+            q = __ldg(c0);
+            if (c0 < last) nxt = __ldg(c0 + 1);
+        }
+        p = c0 + 2;
+        const uint32_t ws = pos >> 2;
+        w = ws == 0 ? q.x : ws == 1 ? q.y : ws == 2 ? q.z : q.w;
+        x = ws == 0 ? q.y : ws == 1 ? q.z : q.w;
+        y = ws == 0 ? q.z : q.w;
+        z = q.w;
+        w >>= 8 * (pos & 3);
+    }
+    __device__ __forceinline__ uint32_t next() {
+        const uint32_t sym = w & 0xFFu;
+        w >>= 8;
+        ++pos;
+        if ((pos & 3) == 0) {
+            if ((pos & 15) == 0) {
+                w = nxt.x; x = nxt.y; y = nxt.z; z = nxt.w;
+                if (p <= last) nxt = __ldg(p);
+                ++p;
+            } else {
+                w = x; x = y; y = z;
+            }
+        }
+        return sym;
+    }
+};
+
+// One coding step of the encoder (src/codec.rs:55-89): narrow the interval to [cl, ch) / count,
+// renormalise in closed form, emit the settled bits.  Returns the number of shifts.
+template <int CLS>
+__device__ __forceinline__ uint32_t encode_step(typename Cls<CLS>::S &low, typename Cls<CLS>::S &high,
+                                                uint32_t &pend, BitSink &sink, uint32_t cl, uint32_t ch,
+                                                uint32_t count, const typename Cls<CLS>::M &g, uint32_t c)
+{
+    using C = Cls<CLS>;
+    using S = typename C::S;
+    using P = typename C::P;
+    const S rm1 = high - low;                                      // range - 1  (:58)
+    const P nh = C::mulr(ch, rm1), nl = C::mulr(cl, rm1);
+    const S h2 = low + (S)C::divc(nh, g, count) - 1;               // :59
+    const S l2 = low + (S)C::divc(nl, g, count);                   // :60
+    const Renorm<S> r = renorm<S>(l2, h2, c);                      // :62-89
+    if (r.n1) {
+        sink.put_code((uint64_t)(l2 >> (c - r.n1)), r.n1, pend);
+        pend = r.k;
+    } else {
+        pend += r.k;
+    }
+    low = r.low; high = r.high;
+    return r.n1 + r.k;
+}
 
 // ------------------------------------------------------------------ encoder
 template <typename TW, int CLS>
@@ -177,7 +271,6 @@ encode_lane_kernel(const LaneEncJob job)
 {
     using C = Cls<CLS>;
     using S = typename C::S;
-    using P = typename C::P;
     using M = typename C::M;
     extern __shared__ uint4 smem_u4[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -185,80 +278,49 @@ encode_lane_kernel(const LaneEncJob job)
     if (blk >= job.n_blocks) return;
 
     LaneTable<TW> tab;
-    tab.t = reinterpret_cast<TW *>(smem_u4) + (size_t)warp * kTabNodes * 32 + lane;
+    tab.init(smem_u4, warp, lane);
     tab.clear();
 
     const uint64_t off = job.in_off[blk];
     const uint32_t len = (uint32_t)(job.in_off[blk + 1] - off);
-    const uintptr_t addr = (uintptr_t)(job.in + off);
-    const uint4 *p16 = reinterpret_cast<const uint4 *>(addr & ~(uintptr_t)15);
-    const uint32_t skip = (uint32_t)(addr & 15);
-
     const uint32_t c = job.c;
     const S maxv = (S)((c == sizeof(S) * 8) ? ~(S)0 : ((((S)1) << c) - 1));
     const M *magic = reinterpret_cast<const M *>(job.magic);
     const uint32_t tcap = job.tcap;
 
-    S low = 0, high = maxv;
-    uint32_t pend = 0;
+    ByteSource src;
+    src.init(job.in + off, len);
     BitSink sink;
     sink.init(job.slots + blk * job.slot_stride);
+    S low = 0, high = maxv;
+    uint32_t pend = 0;
 
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    if (len) cur = __ldg(p16);
-
-    for (uint32_t t = 0; t <= len; ++t) {
-        const bool is_eof = (t == len);
-        const uint32_t tt = t < tcap ? t : tcap;
-        const uint32_t count = kNsym + tt;
-        const M g = C::ldm(magic + tt);
+    // adaptive phase: the model still learns, count grows by one per symbol
+    const uint32_t n_adapt = len < tcap ? len : tcap;
+    uint32_t t = 0;
+    for (; t < n_adapt; ++t) {
+        const M g = C::ldm(magic + t);
+        const uint32_t sym = src.next();
         uint32_t cl, ch;
-        if (!is_eof) {
-            const uint32_t gpos = skip + t;
-            if ((gpos & 15) == 0 && t) cur = __ldg(p16 + (gpos >> 4));
-            const uint32_t ws = (gpos >> 2) & 3;
-            const uint32_t wv = ws == 0 ? cur.x : ws == 1 ? cur.y : ws == 2 ? cur.z : cur.w;
-            const uint32_t sym = (wv >> ((gpos & 3) * 8)) & 0xFFu;
-            tab.query(sym, tt, cl, ch);
-            if (t < tcap) tab.update(sym);
-        } else {
-            cl = count - 1;      // cum(256) = total - freq(EOF), EOF's frequency never grows
-            ch = count;
-        }
-        // src/codec.rs:58-60
-        const S rm1 = high - low;
-        const P nh = C::mulr(ch, rm1), nl = C::mulr(cl, rm1);
-        high = low + (S)C::divc(nh, g, count) - 1;
-        low = low + (S)C::divc(nl, g, count);
-        // src/codec.rs:62-89 in closed form
-        const Renorm<S> r = renorm<S>(low, high, c);
-        if (r.n1) {
-            if (sizeof(S) == 4 || r.n1 <= 32) {
-                sink.put_with_pending((uint32_t)(low >> (c - r.n1)), r.n1, pend);
-            } else {   // c > 32 only: more than 32 common bits
-                const uint32_t hi_n = r.n1 - 32;
-                sink.put_with_pending((uint32_t)((uint64_t)low >> (c - hi_n)), hi_n, pend);
-                sink.put((uint32_t)((uint64_t)low >> (c - r.n1)), 32);
-            }
-            pend = r.k;
-        } else {
-            pend += r.k;
-        }
-        low = r.low; high = r.high;
-        if (is_eof) {
-            // src/codec.rs:91-99: the remaining `extra` MSBs of low, then flush
-            const uint32_t extra = c - (r.n1 + r.k);
-            if (extra) {
-                if (sizeof(S) == 4 || extra <= 32) {
-                    sink.put_with_pending((uint32_t)(low >> (c - extra)), extra, pend);
-                } else {
-                    const uint32_t hi_n = extra - 32;
-                    sink.put_with_pending((uint32_t)((uint64_t)low >> (c - hi_n)), hi_n, pend);
-                    sink.put((uint32_t)((uint64_t)low >> (c - extra)), 32);
-                }
-            }
-        }
+        tab.query(sym, t, cl, ch);
+        tab.update(sym);
+        encode_step<CLS>(low, high, pend, sink, cl, ch, kNsym + t, g, c);
     }
+    // frozen phase (adaptive_tree.rs:84): total == FMAX, table and reciprocal are constant
+    const uint32_t tt = n_adapt;                          // updates done = min(len, tcap)
+    const M gf = C::ldm(magic + tt);
+    const uint32_t countf = kNsym + tt;
+    for (; t < len; ++t) {
+        const uint32_t sym = src.next();
+        uint32_t cl, ch;
+        tab.query(sym, tt, cl, ch);
+        encode_step<CLS>(low, high, pend, sink, cl, ch, countf, gf, c);
+    }
+    // EOF symbol: cum(256) = total - 1 (EOF's own frequency never grows), then the tail of
+    // src/codec.rs:91-99: the remaining `extra` MSBs of low, then flush.
+    const uint32_t shifts = encode_step<CLS>(low, high, pend, sink, countf - 1, countf, countf, gf, c);
+    const uint32_t extra = c - shifts;
+    if (extra) sink.put_code((uint64_t)(low >> (c - extra)), extra, pend);
     job.sizes[blk] = sink.finish();
     job.status[blk] = 0;
 }
@@ -346,7 +408,7 @@ decode_lane_kernel(const LaneDecJob job)
     if (blk >= job.n_blocks) return;
 
     LaneTable<TW> tab;
-    tab.t = reinterpret_cast<TW *>(smem_u4) + (size_t)warp * kTabNodes * 32 + lane;
+    tab.init(smem_u4, warp, lane);
     tab.clear();
 
     const uint64_t coff = job.comp_off[blk];
@@ -379,22 +441,29 @@ decode_lane_kernel(const LaneDecJob job)
         // src/codec.rs:129-131 without the division: find i with cum(i)*range <= X < cum(i+1)*range,
         // X = (value-low+1)*count - 1.
         const S rm1 = high - low;
-        const P X = C::mulr(count, (S)(value - low)) - 1;      // (value-low+1)*count - 1
+        const P X = C::mulr(count, (S)(value - low)) - 1;
         // step m = 256: node 256 = count-1 (adaptive_tree.rs:119-127 with the unstored node)
         P plo = 0, phi = C::mulr(count - 1, rm1);
         uint32_t sym;
         if (X >= phi) {
             sym = kEof; plo = phi; phi = C::mulr(count, rm1);
         } else {
-            uint32_t i = 0;
+            uint32_t I = 0;                                       // i * 32
 #pragma unroll
-            for (int m = 128; m >= 1; m >>= 1) {
-                const uint32_t ti = i + m;
-                const uint32_t tv = (uint32_t)m + tab.ld(ti);
+            for (int m = 128; m >= 2; m >>= 1) {                  // even nodes i + m
+                const uint32_t TI = I + (uint32_t)(m << 5);
+                const uint32_t tv = (uint32_t)m + tab.t[TI];
                 const P p = plo + C::mulr(tv, rm1);
-                if (X >= p) { i = ti; plo = p; } else { phi = p; }
+                const bool right = X >= p;
+                I = right ? TI : I; plo = right ? p : plo; phi = right ? phi : p;
             }
-            sym = i;
+            {                                                     // m = 1: odd node i + 1
+                const uint32_t tv = 1u + tab.t[(int)I + 32 + LaneTable<TW>::kOddAdj];
+                const P p = plo + C::mulr(tv, rm1);
+                const bool right = X >= p;
+                I = right ? I + 32u : I; plo = right ? p : plo; phi = right ? phi : p;
+            }
+            sym = I >> 5;
         }
         // src/codec.rs:133-134
         high = low + (S)C::divc(phi, g, count) - 1;
@@ -408,7 +477,7 @@ decode_lane_kernel(const LaneDecJob job)
         if (t >= cap) { st = 6; break; }                            // sink full
         const S chunk = (S)src.take64(n);
         S v1 = (r.n1 >= sizeof(S) * 8) ? (S)0 : (S)((value << r.n1) & maxv);
-        v1 |= (r.k >= sizeof(S) * 8) ? (S)0 : (S)(chunk >> r.k);
+        v1 |= (S)(chunk >> r.k);
         value = (v1 & half) | ((S)(v1 << r.k) & body) | (chunk & (S)((((S)1) << r.k) - 1));
         low = r.low; high = r.high;
         out.put(t, sym);
