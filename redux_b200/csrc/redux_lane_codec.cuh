@@ -66,6 +66,7 @@ template <int CLS> struct Cls;
 template <> struct Cls<kNarrow> {
     using S = uint32_t; using P = uint32_t; using M = Magic32;
     static __device__ __forceinline__ P mulr(uint32_t v, S rm1) { return v * rm1 + v; }   // v * range
+    static __device__ __forceinline__ P mul_add(uint32_t v, S rm1, P acc) { return v * (rm1 + 1u) + acc; }
     static __device__ __forceinline__ P divc(P n, const M &g, uint32_t) { return div_magic32(n, g); }
     static __device__ __forceinline__ M ldm(const M *p) {
         uint2 v = __ldg(reinterpret_cast<const uint2 *>(p)); M g; g.m = v.x; g.sh = v.y; return g;
@@ -74,6 +75,7 @@ template <> struct Cls<kNarrow> {
 template <> struct Cls<kWide> {
     using S = uint32_t; using P = uint64_t; using M = Magic64;
     static __device__ __forceinline__ P mulr(uint32_t v, S rm1) { return (uint64_t)v * rm1 + v; }
+    static __device__ __forceinline__ P mul_add(uint32_t v, S rm1, P acc) { return (uint64_t)v * rm1 + (acc + v); }
     static __device__ __forceinline__ P divc(P n, const M &g, uint32_t) { return div_magic64(n, g); }
     static __device__ __forceinline__ M ldm(const M *p) {
         uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
@@ -83,6 +85,7 @@ template <> struct Cls<kWide> {
 template <> struct Cls<kHuge> {
     using S = uint64_t; using P = uint64_t; using M = Magic64;
     static __device__ __forceinline__ P mulr(uint32_t v, S rm1) { return (uint64_t)v * rm1 + v; }
+    static __device__ __forceinline__ P mul_add(uint32_t v, S rm1, P acc) { return (uint64_t)v * (rm1 + 1u) + acc; }
     static __device__ __forceinline__ P divc(P n, const M &, uint32_t count) { return n / count; }
     static __device__ __forceinline__ M ldm(const M *) { M g; g.m = 0; g.sh = 0; g.pad = 0; return g; }
 };
@@ -326,33 +329,41 @@ encode_lane_kernel(const LaneEncJob job)
 }
 
 // ------------------------------------------------------------------ bit source (decoder input)
+// Aligned 32-bit words, byte-swapped into a 64-bit bit buffer.  The word after the one being
+// consumed is always already in flight (`nxt`), so a refill never waits on memory.
 struct BitSource {
     uint64_t bb;            // bit buffer, valid bits are the low `bn`
     uint32_t bn;
-    const uint32_t *w;      // aligned words
-    uint32_t widx, nwords;
-    uint64_t used, total;   // bits
+    uint32_t nxt;           // prefetched next word, bits in stream order
+    const uint32_t *w;      // word after nxt
+    const uint32_t *wend;   // one past the last word that may be read
+    uint32_t left;          // stream bits not yet consumed (streams are < 2^29 bytes here)
+    uint32_t total;
 
-    __device__ __forceinline__ void init(const uint8_t *src, uint64_t len) {
+    static __device__ __forceinline__ uint32_t ldw(const uint32_t *p) { return __byte_perm(__ldg(p), 0, 0x0123); }
+    __device__ __forceinline__ void init(const uint8_t *src, uint32_t len) {
         const uintptr_t a = (uintptr_t)src;
         const uint32_t mis = (uint32_t)(a & 3);
         w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-        nwords = (uint32_t)((mis + len + 3) >> 2);
-        used = 0; total = len * 8;
-        bb = 0; bn = 0; widx = 0;
-        if (nwords) { bb = __byte_perm(__ldg(w), 0, 0x0123); bn = 32 - 8 * mis; widx = 1; }
+        wend = w + ((mis + len + 3) >> 2);
+        total = left = len * 8;
+        bb = 0; bn = 0; nxt = 0;
+        if (w < wend) { bb = ldw(w); bn = 32 - 8 * mis; ++w; }
+        if (w < wend) nxt = ldw(w);
+        ++w;
     }
-    __device__ __forceinline__ bool has(uint32_t n) const { return used + n <= total; }
+    __device__ __forceinline__ bool has(uint32_t n) const { return n <= left; }
+    __device__ __forceinline__ uint32_t used() const { return total - left; }
     // next n (0..32) bits, MSB first (src/bitio/mod.rs:78-120); caller checked has(n)
     __device__ __forceinline__ uint32_t take(uint32_t n) {
         if (bn < n) {
-            uint32_t x = (widx < nwords) ? __byte_perm(__ldg(w + widx), 0, 0x0123) : 0u;
-            ++widx;
-            bb = (bb << 32) | x;
+            bb = (bb << 32) | nxt;
             bn += 32;
+            nxt = (w < wend) ? ldw(w) : 0u;
+            ++w;
         }
         bn -= n;
-        used += n;
+        left -= n;
         const uint32_t mask = n ? (0xFFFFFFFFu >> (32 - n)) : 0u;
         return (uint32_t)(bb >> bn) & mask;
     }
@@ -367,126 +378,145 @@ struct BitSource {
 // Decoded symbols leave as aligned 32-bit words; the (possibly unaligned) head and tail of a
 // block's slot are written byte-wise so neighbouring blocks are never touched.
 struct ByteSink {
-    uintptr_t dst;
-    uint32_t wacc;
-    __device__ __forceinline__ void init(uint8_t *d) { dst = (uintptr_t)d; wacc = 0; }
+    uintptr_t dst, pw;      // slot start, current (aligned) word
+    uint32_t wacc, sh;
+    __device__ __forceinline__ void init(uint8_t *d) {
+        dst = (uintptr_t)d; pw = dst & ~(uintptr_t)3; wacc = 0; sh = 8 * (uint32_t)(dst & 3);
+    }
     __device__ __forceinline__ void store_bytes(uintptr_t from, uintptr_t to) const {
         for (uintptr_t p = from; p < to; ++p)
             *reinterpret_cast<uint8_t *>(p) = (uint8_t)(wacc >> (8 * (p & 3)));
     }
-    __device__ __forceinline__ void put(uint64_t t, uint32_t sym) {
-        const uintptr_t a = dst + t;
-        const uint32_t pos = (uint32_t)(a & 3);
-        wacc |= sym << (8 * pos);
-        if (pos == 3) {
-            if (a - 3 >= dst) *reinterpret_cast<uint32_t *>(a - 3) = wacc;
-            else store_bytes(dst, a + 1);
-            wacc = 0;
+    __device__ __forceinline__ void put(uint32_t sym) {
+        wacc |= sym << sh;
+        sh += 8;
+        if (sh == 32) {
+            if (pw >= dst) *reinterpret_cast<uint32_t *>(pw) = wacc;
+            else store_bytes(dst, pw + 4);
+            pw += 4; wacc = 0; sh = 0;
         }
     }
-    __device__ __forceinline__ void finish(uint64_t n) const {
-        const uintptr_t end = dst + n;
-        if (end & 3) {
-            const uintptr_t ws = end & ~(uintptr_t)3;
-            store_bytes(ws > dst ? ws : dst, end);
-        }
+    __device__ __forceinline__ void finish() const {
+        if (sh) store_bytes(pw > dst ? pw : dst, pw + (sh >> 3));
     }
 };
 
 // ------------------------------------------------------------------ decoder
 template <typename TW, int CLS>
-__global__ void __launch_bounds__(kLaneThreads, 2)
-decode_lane_kernel(const LaneDecJob job)
-{
+struct LaneDecoder {
     using C = Cls<CLS>;
     using S = typename C::S;
     using P = typename C::P;
     using M = typename C::M;
+    LaneTable<TW> tab;
+    BitSource src;
+    ByteSink out;
+    S low, high, value, maxv;
+    uint32_t c, t, cap;
+    int32_t st;          // 0 running, -1 EOF symbol decoded (success), >0 error code
+
+    // Decodes symbols while t < t_end.  ADAPT: the model still learns (count = 257 + t, one reciprocal
+    // per position); otherwise the table is frozen at `count`.
+    template <bool ADAPT>
+    __device__ __forceinline__ void run(uint32_t t_end, const M *magic, uint32_t count_frozen, const M &g_frozen) {
+        const S body = maxv >> 1, half = body + 1;
+        while (t < t_end) {
+            const uint32_t count = ADAPT ? kNsym + t : count_frozen;
+            const M g = ADAPT ? C::ldm(magic + t) : g_frozen;
+            // src/codec.rs:129-131 without the division: find i with cum(i)*range <= X < cum(i+1)*range,
+            // X = (value-low+1)*count - 1.
+            const S rm1 = high - low;
+            const P X = C::mulr(count, (S)(value - low)) - 1;
+            // step m = 256: node 256 = count-1 (adaptive_tree.rs:119-127 with the unstored node)
+            P plo = 0, phi = C::mulr(count - 1, rm1);
+            uint32_t I = 0;                                       // i * 32
+            const bool is_eof = X >= phi;
+#pragma unroll
+            for (int m = 128; m >= 2; m >>= 1) {                  // even nodes i + m
+                const uint32_t tv = (uint32_t)m + tab.t[I + (uint32_t)(m << 5)];
+                const P p = C::mul_add(tv, rm1, plo);
+                const bool right = X >= p;
+                if (right) { I += (uint32_t)(m << 5); plo = p; } else { phi = p; }
+            }
+            {                                                     // m = 1: odd node i + 1
+                const uint32_t tv = 1u + tab.t[(int)I + 32 + LaneTable<TW>::kOddAdj];
+                const P p = C::mul_add(tv, rm1, plo);
+                const bool right = X >= p;
+                if (right) { I += 32u; plo = p; } else { phi = p; }
+            }
+            if (is_eof) {                                         // src/codec.rs:136-138: no renorm, no reads
+                st = -1;
+                return;
+            }
+            const uint32_t sym = I >> 5;
+            // src/codec.rs:133-134
+            high = low + (S)C::divc(phi, g, count) - 1;
+            low = low + (S)C::divc(plo, g, count);
+            if (ADAPT) tab.update(sym);
+            // src/codec.rs:140-158 in closed form
+            const Renorm<S> r = renorm<S>(low, high, c);
+            const uint32_t n = r.n1 + r.k;
+            if (!src.has(n)) { st = 1; src.left = 0; return; }    // Err(Eof) inside get_bit
+            if (t >= cap) { st = 6; return; }                     // sink full
+            const S chunk = (S)src.take64(n);
+            S v1 = (r.n1 >= sizeof(S) * 8) ? (S)0 : (S)((value << r.n1) & maxv);
+            v1 |= (S)(chunk >> r.k);
+            value = (v1 & half) | ((S)(v1 << r.k) & body) | (chunk & (S)((((S)1) << r.k) - 1));
+            low = r.low; high = r.high;
+            out.put(sym);
+            ++t;
+        }
+    }
+};
+
+template <typename TW, int CLS>
+__global__ void __launch_bounds__(kLaneThreads, 2)
+decode_lane_kernel(const LaneDecJob job)
+{
+    using D = LaneDecoder<TW, CLS>;
+    using S = typename D::S;
+    using M = typename D::M;
     extern __shared__ uint4 smem_u4[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t blk = (uint64_t)blockIdx.x * kLaneThreads + threadIdx.x;
     if (blk >= job.n_blocks) return;
 
-    LaneTable<TW> tab;
-    tab.init(smem_u4, warp, lane);
-    tab.clear();
+    D d;
+    d.tab.init(smem_u4, warp, lane);
+    d.tab.clear();
 
     const uint64_t coff = job.comp_off[blk];
     const uint64_t clen = job.comp_off[blk + 1] - coff;
     const uint64_t roff = job.raw_off[blk];
-    const uint64_t cap = job.raw_off[blk + 1] - roff;
-
-    const uint32_t c = job.c;
-    const S maxv = (S)((c == sizeof(S) * 8) ? ~(S)0 : ((((S)1) << c) - 1));
-    const S body = maxv >> 1, half = body + 1;
+    const uint64_t cap64 = job.raw_off[blk + 1] - roff;
+    if (clen >= (1ull << 29)) {                 // 32-bit bit counters; such a stream is not lane work
+        job.raw_len[blk] = 0; job.consumed[blk] = 0; job.status[blk] = 5;
+        return;
+    }
+    d.c = job.c;
+    d.maxv = (S)((d.c == sizeof(S) * 8) ? ~(S)0 : ((((S)1) << d.c) - 1));
+    d.cap = cap64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)cap64;
+    d.src.init(job.comp + coff, (uint32_t)clen);
+    d.out.init(job.raw + roff);
+    d.st = 0; d.t = 0;
+    d.low = 0; d.high = d.maxv; d.value = 0;
     const M *magic = reinterpret_cast<const M *>(job.magic);
     const uint32_t tcap = job.tcap;
 
-    BitSource src;
-    src.init(job.comp + coff, clen);
-    ByteSink out;
-    out.init(job.raw + roff);
-
-    int32_t st = 0;
-    uint64_t t = 0;
-    S low = 0, high = maxv, value = 0;
     // src/codec.rs:124-127: prime code_bits bits
-    if (!src.has(c)) { st = 1; src.used = src.total; }
-    else value = (S)src.take64(c);
+    if (!d.src.has(d.c)) { d.st = 1; d.src.left = 0; }
+    else d.value = (S)d.src.take64(d.c);
 
-    while (st == 0) {
-        const uint32_t tt = t < tcap ? (uint32_t)t : tcap;
-        const uint32_t count = kNsym + tt;
-        const M g = C::ldm(magic + tt);
-        // src/codec.rs:129-131 without the division: find i with cum(i)*range <= X < cum(i+1)*range,
-        // X = (value-low+1)*count - 1.
-        const S rm1 = high - low;
-        const P X = C::mulr(count, (S)(value - low)) - 1;
-        // step m = 256: node 256 = count-1 (adaptive_tree.rs:119-127 with the unstored node)
-        P plo = 0, phi = C::mulr(count - 1, rm1);
-        uint32_t sym;
-        if (X >= phi) {
-            sym = kEof; plo = phi; phi = C::mulr(count, rm1);
-        } else {
-            uint32_t I = 0;                                       // i * 32
-#pragma unroll
-            for (int m = 128; m >= 2; m >>= 1) {                  // even nodes i + m
-                const uint32_t TI = I + (uint32_t)(m << 5);
-                const uint32_t tv = (uint32_t)m + tab.t[TI];
-                const P p = plo + C::mulr(tv, rm1);
-                const bool right = X >= p;
-                I = right ? TI : I; plo = right ? p : plo; phi = right ? phi : p;
-            }
-            {                                                     // m = 1: odd node i + 1
-                const uint32_t tv = 1u + tab.t[(int)I + 32 + LaneTable<TW>::kOddAdj];
-                const P p = plo + C::mulr(tv, rm1);
-                const bool right = X >= p;
-                I = right ? I + 32u : I; plo = right ? p : plo; phi = right ? phi : p;
-            }
-            sym = I >> 5;
-        }
-        // src/codec.rs:133-134
-        high = low + (S)C::divc(phi, g, count) - 1;
-        low = low + (S)C::divc(plo, g, count);
-        if (sym == kEof) break;                                  // src/codec.rs:136-138
-        if (t < tcap) tab.update(sym);
-        // src/codec.rs:140-158 in closed form
-        const Renorm<S> r = renorm<S>(low, high, c);
-        const uint32_t n = r.n1 + r.k;
-        if (!src.has(n)) { st = 1; src.used = src.total; break; }   // Err(Eof) inside get_bit
-        if (t >= cap) { st = 6; break; }                            // sink full
-        const S chunk = (S)src.take64(n);
-        S v1 = (r.n1 >= sizeof(S) * 8) ? (S)0 : (S)((value << r.n1) & maxv);
-        v1 |= (S)(chunk >> r.k);
-        value = (v1 & half) | ((S)(v1 << r.k) & body) | (chunk & (S)((((S)1) << r.k) - 1));
-        low = r.low; high = r.high;
-        out.put(t, sym);
-        ++t;
+    const M g0 = D::C::ldm(magic);
+    if (d.st == 0) d.template run<true>(tcap, magic, 0, g0);
+    if (d.st == 0) {
+        const M gf = D::C::ldm(magic + tcap);
+        d.template run<false>(0xFFFFFFFFu, magic, kNsym + tcap, gf);
     }
-    out.finish(t);
-    job.raw_len[blk] = t;
-    job.consumed[blk] = (src.used + 7) >> 3;
-    job.status[blk] = st;
+    d.out.finish();
+    job.raw_len[blk] = d.t;
+    job.consumed[blk] = (d.src.used() + 7) >> 3;
+    job.status[blk] = d.st < 0 ? 0 : d.st;
 }
 
 }  // namespace rdx
