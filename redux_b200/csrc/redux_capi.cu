@@ -127,7 +127,7 @@ int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, P
     pl->tcap = (uint32_t)(fmax - kNsym);                       // f <= 31 -> fits
     const uint64_t updates = std::min<uint64_t>(max_block_len, pl->tcap);
     pl->wide_table = updates > 65536;                          // u16 increments suffice otherwise
-    pl->magic_len = (uint32_t)updates + 1;
+    pl->magic_len = (uint32_t)updates + 2;                   // positions 0..updates, +1 read-ahead
     const uint64_t bound = redux_compress_bound(max_block_len, pl->c);
     pl->slot_stride = ((bound + 15) & ~(uint64_t)15) + 16;
     return REDUX_OK;

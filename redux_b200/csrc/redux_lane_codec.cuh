@@ -215,8 +215,8 @@ struct ByteSource {
         nxt = q;
         if (len) {
             q = __ldg(c0);
-            if (c0 < last) nxt = __ldg(c0 + 1);
-        }
+            nxt = __ldg(c0 < last ? c0 + 1 : last);
+        }                                   // len == 0: next() is never called, nothing is loaded
         p = c0 + 2;
         const uint32_t ws = pos >> 2;
         w = ws == 0 ? q.x : ws == 1 ? q.y : ws == 2 ? q.z : q.w;
@@ -232,7 +232,7 @@ struct ByteSource {
         if ((pos & 3) == 0) {
             if ((pos & 15) == 0) {
                 w = nxt.x; x = nxt.y; y = nxt.z; z = nxt.w;
-                if (p <= last) nxt = __ldg(p);
+                nxt = __ldg(p <= last ? p : last);   // past the end: re-read the last chunk, never consumed
                 ++p;
             } else {
                 w = x; x = y; y = z;
@@ -301,8 +301,10 @@ encode_lane_kernel(const LaneEncJob job)
     // adaptive phase: the model still learns, count grows by one per symbol
     const uint32_t n_adapt = len < tcap ? len : tcap;
     uint32_t t = 0;
+    M gn = C::ldm(magic);                                  // reciprocal of position t, loaded one ahead
     for (; t < n_adapt; ++t) {
-        const M g = C::ldm(magic + t);
+        const M g = gn;
+        gn = C::ldm(magic + t + 1);
         const uint32_t sym = src.next();
         uint32_t cl, ch;
         tab.query(sym, t, cl, ch);
@@ -311,7 +313,7 @@ encode_lane_kernel(const LaneEncJob job)
     }
     // frozen phase (adaptive_tree.rs:84): total == FMAX, table and reciprocal are constant
     const uint32_t tt = n_adapt;                          // updates done = min(len, tcap)
-    const M gf = C::ldm(magic + tt);
+    const M gf = gn;                                      // = magic[tt]
     const uint32_t countf = kNsym + tt;
     for (; t < len; ++t) {
         const uint32_t sym = src.next();
@@ -334,32 +336,37 @@ encode_lane_kernel(const LaneEncJob job)
 struct BitSource {
     uint64_t bb;            // bit buffer, valid bits are the low `bn`
     uint32_t bn;
-    uint32_t nxt;           // prefetched next word, bits in stream order
+    uint32_t nxt;           // prefetched next word, still in memory byte order (swapped when consumed,
+                            // so that nothing depends on the load until the next refill)
     const uint32_t *w;      // word after nxt
-    const uint32_t *wend;   // one past the last word that may be read
+    const uint32_t *wlast;  // last word that may be read
     uint32_t left;          // stream bits not yet consumed (streams are < 2^29 bytes here)
     uint32_t total;
 
-    static __device__ __forceinline__ uint32_t ldw(const uint32_t *p) { return __byte_perm(__ldg(p), 0, 0x0123); }
+    static __device__ __forceinline__ uint32_t swap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
     __device__ __forceinline__ void init(const uint8_t *src, uint32_t len) {
         const uintptr_t a = (uintptr_t)src;
         const uint32_t mis = (uint32_t)(a & 3);
         w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-        wend = w + ((mis + len + 3) >> 2);
+        wlast = w + ((mis + len + 3) >> 2) - 1;
         total = left = len * 8;
         bb = 0; bn = 0; nxt = 0;
-        if (w < wend) { bb = ldw(w); bn = 32 - 8 * mis; ++w; }
-        if (w < wend) nxt = ldw(w);
-        ++w;
+        if (len) {
+            bb = swap(__ldg(w)); bn = 32 - 8 * mis;
+            nxt = __ldg(w + 1 <= wlast ? w + 1 : wlast);
+        } else {
+            wlast = w;                      // never dereferenced: has() fails before any take()
+        }
+        w += 2;
     }
     __device__ __forceinline__ bool has(uint32_t n) const { return n <= left; }
     __device__ __forceinline__ uint32_t used() const { return total - left; }
     // next n (0..32) bits, MSB first (src/bitio/mod.rs:78-120); caller checked has(n)
     __device__ __forceinline__ uint32_t take(uint32_t n) {
         if (bn < n) {
-            bb = (bb << 32) | nxt;
+            bb = (bb << 32) | swap(nxt);
             bn += 32;
-            nxt = (w < wend) ? ldw(w) : 0u;
+            nxt = __ldg(w <= wlast ? w : wlast);   // past the end: re-read the last word, never consumed
             ++w;
         }
         bn -= n;
@@ -420,9 +427,11 @@ struct LaneDecoder {
     template <bool ADAPT>
     __device__ __forceinline__ void run(uint32_t t_end, const M *magic, uint32_t count_frozen, const M &g_frozen) {
         const S body = maxv >> 1, half = body + 1;
+        M gn = ADAPT ? C::ldm(magic + t) : g_frozen;          // reciprocal of position t, loaded one ahead
         while (t < t_end) {
             const uint32_t count = ADAPT ? kNsym + t : count_frozen;
-            const M g = ADAPT ? C::ldm(magic + t) : g_frozen;
+            const M g = gn;
+            if (ADAPT) gn = C::ldm(magic + t + 1);
             // src/codec.rs:129-131 without the division: find i with cum(i)*range <= X < cum(i+1)*range,
             // X = (value-low+1)*count - 1.
             const S rm1 = high - low;
