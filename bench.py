@@ -185,6 +185,7 @@ def run_ours(a):
     import torch
 
     import redux_b200 as rb
+    from redux_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -207,7 +208,7 @@ def run_ours(a):
     n, L = a.blocks, a.block_len
     ctx = rb.Context([local])
     stream = torch.cuda.current_stream().cuda_stream
-    first_block = rank * n
+    first_block = sharding.weak_first_block(n, rank)      # weak scaling: distinct blocks per rank
 
     # ---- synthetic batch, resident in HBM
     raw = torch.empty(n * L, dtype=torch.uint8, device="cuda")
@@ -262,10 +263,7 @@ def run_ours(a):
     ctx.timing_enable(False)
 
     t_step = (t_enc + t_dec) / a.steps
-    tt = torch.tensor([t_step, t_enc / a.steps, t_dec / a.steps], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_step, t_e, t_d = (float(x) for x in tt.cpu())
+    t_step, t_e, t_d = sharding.max_over_ranks([t_step, t_enc / a.steps, t_dec / a.steps], dist, "cuda")
     raw_bytes = n * L
     value = world * raw_bytes / t_step / 1e6
 
@@ -309,10 +307,7 @@ def run_ours(a):
         torch.cuda.synchronize()
         t_e2e = (time.perf_counter() - t0) / ksteps
         assert (np_back == np_raw).all()
-        te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        t_e2e = float(te.cpu()[0])
+        t_e2e = sharding.max_over_ranks([t_e2e], dist, "cuda")[0]
         meta = 8 * (n + 1)
         e2e = {"value": round(world * raw_bytes / t_e2e / 1e6, 2), "unit": UNIT,
                "h2d_bytes_per_step": raw_bytes + meta + cb + 2 * meta,

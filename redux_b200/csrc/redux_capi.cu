@@ -266,6 +266,13 @@ extern "C" void redux_debug_renorm(uint64_t low, uint64_t high, uint32_t c, uint
     else         { Renorm<uint64_t> r = renorm<uint64_t>(low, high, c); *n1 = r.n1; *k = r.k; *nl = r.low; *nh = r.high; }
 }
 
+extern "C" void redux_debug_shard(uint64_t n_blocks, uint32_t n_devices, uint32_t g, uint64_t *first, uint64_t *count)
+{
+    // the partition rule of the host front end (make_shards below)
+    const uint64_t a = n_blocks * g / n_devices, b = n_blocks * (g + 1) / n_devices;
+    *first = a; *count = b - a;
+}
+
 extern "C" void redux_generate_blocks_host(uint8_t *out, uint64_t first_block, uint64_t n_blocks,
                                            uint64_t block_len, uint64_t seed)
 {
