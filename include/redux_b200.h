@@ -120,7 +120,8 @@ int redux_encode_batch(redux_ctx_t *ctx, int model_kind, const redux_params_t *p
 /* decode: stream i = comp[comp_offsets[i] .. comp_offsets[i+1]); its symbols go to
  *   raw[raw_offsets[i] ..) with capacity raw_offsets[i+1]-raw_offsets[i]; raw_lens[i] = bytes written
  *   (second tuple element of decompress()), consumed[i] = compressed bytes read (first element).
- *   A truncated stream gives status REDUX_EOF with the bytes decoded so far left in place. */
+ *   A truncated stream gives status REDUX_EOF with the bytes decoded so far left in place; bytes beyond
+ *   raw_lens[i] inside slot i are unspecified. */
 int redux_decode_batch(redux_ctx_t *ctx, int model_kind, const redux_params_t *params,
                        const uint8_t *comp, const uint64_t *comp_offsets, uint64_t n_blocks,
                        uint8_t *raw, const uint64_t *raw_offsets, uint64_t *raw_lens,

@@ -39,9 +39,28 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Grow-only pinned host buffer (small bookkeeping arrays of the pipelined host API).
+struct HostBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaHostAlloc(&p, bytes + (bytes >> 2), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes + (bytes >> 2);
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+constexpr int kPipeStreams = 16;          // one compute stream per chunk in flight (host-buffer API)
+
 struct DeviceState {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t pipe[kPipeStreams] = {};
+    cudaStream_t copy = nullptr;          // device-to-host stream of the encode pipeline
+    cudaStream_t h2d = nullptr;           // host-to-device stream: input copies never queue behind kernels
+    HostBuf pin_off, pin_status, pin_aux0, pin_aux1;
     DevBuf slots, sizes, flag;                 // encoder workspace
     DevBuf st_in, st_off, st_out, st_ooff, st_status, st_aux0, st_aux1, st_roff;   // host-API staging
     uint8_t *text_lut = nullptr;
@@ -314,7 +333,11 @@ extern "C" int redux_ctx_create(const int *devices, int n_devices, redux_ctx_t *
         cudaDeviceProp prop;
         if (!g.ok || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { redux_ctx_destroy(ctx); return REDUX_CUDA_ERROR; }
         if (prop.major < 10) { redux_ctx_destroy(ctx); return REDUX_CUDA_ERROR; }   // sm_100a binary only
-        if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        bool streams_ok = cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking) == cudaSuccess &&
+                          cudaStreamCreateWithFlags(&d.h2d, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < kPipeStreams && streams_ok; ++i)
+            streams_ok = cudaStreamCreateWithFlags(&d.pipe[i], cudaStreamNonBlocking) == cudaSuccess;
+        if (!streams_ok || cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
             configure_kernels() != cudaSuccess ||
             cudaMalloc((void **)&d.text_lut, 256) != cudaSuccess ||
             cudaMemcpy(d.text_lut, lut, 256, cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -334,7 +357,12 @@ extern "C" void redux_ctx_destroy(redux_ctx_t *ctx)
     if (!ctx) return;
     for (auto &d : ctx->devs) {
         DeviceGuard g(d.device);
-        if (d.stream) { cudaStreamSynchronize(d.stream); cudaStreamDestroy(d.stream); }
+        cudaDeviceSynchronize();
+        if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.copy) cudaStreamDestroy(d.copy);
+        if (d.h2d) cudaStreamDestroy(d.h2d);
+        for (int i = 0; i < kPipeStreams; ++i) if (d.pipe[i]) cudaStreamDestroy(d.pipe[i]);
+        for (HostBuf *b : {&d.pin_off, &d.pin_status, &d.pin_aux0, &d.pin_aux1}) b->release();
         for (DevBuf *b : {&d.slots, &d.sizes, &d.flag, &d.st_in, &d.st_off, &d.st_out, &d.st_ooff,
                           &d.st_status, &d.st_aux0, &d.st_aux1, &d.st_roff}) b->release();
         for (auto &m : d.magics) cudaFree(m.ptr);
@@ -390,6 +418,68 @@ extern "C" int redux_ctx_synchronize(redux_ctx_t *ctx, int device, void *stream)
 }
 
 // ============================================================================ device-resident API
+namespace {
+
+// Enqueues encode + size scan + compaction for n_blocks blocks on stream s.  Workspace slices are given
+// explicitly so that several chunks of one batch can be in flight on different streams.
+int encode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, const void *magic,
+                  const uint8_t *d_in, const uint64_t *d_in_off, uint64_t n_blocks,
+                  uint8_t *d_out, uint64_t out_capacity, uint64_t *d_out_off, int32_t *d_status,
+                  uint8_t *slots, uint32_t *sizes, int32_t *flag)
+{
+    LaneEncJob job;
+    job.in = d_in; job.in_off = d_in_off; job.n_blocks = n_blocks;
+    job.slots = slots; job.slot_stride = pl.slot_stride;
+    job.sizes = sizes; job.status = d_status;
+    job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
+    const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
+    {
+        KernelTimer kt(ctx, device, s, REDUX_KERNEL_ENCODE);
+        if (pl.wide_table) launch_encode<uint32_t>(pl.cls, job, grid, smem, s);
+        else               launch_encode<uint16_t>(pl.cls, job, grid, smem, s);
+    }
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    {
+        KernelTimer kt(ctx, device, s, REDUX_KERNEL_SCAN);
+        scan_sizes_kernel<<<1, kScanThreads, 0, s>>>(sizes, n_blocks, d_out_off, out_capacity, flag);
+    }
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    const uint32_t cgrid = (uint32_t)std::min<uint64_t>(n_blocks, 148 * 16);
+    {
+        KernelTimer kt(ctx, device, s, REDUX_KERNEL_COMPACT);
+        compact_kernel<<<cgrid, kCompactThreads, 0, s>>>(slots, pl.slot_stride, sizes, d_out_off, n_blocks,
+                                                         d_out, out_capacity, d_status);
+    }
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return REDUX_OK;
+}
+
+int decode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, const void *magic,
+                  const uint8_t *d_comp, const uint64_t *d_comp_off, uint64_t n_blocks,
+                  uint8_t *d_raw, const uint64_t *d_raw_off, uint64_t *d_raw_lens, uint64_t *d_consumed,
+                  int32_t *d_status)
+{
+    LaneDecJob job;
+    job.comp = d_comp; job.comp_off = d_comp_off; job.n_blocks = n_blocks;
+    job.raw = d_raw; job.raw_off = d_raw_off; job.raw_len = d_raw_lens; job.consumed = d_consumed;
+    job.status = d_status; job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
+    const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
+    {
+        KernelTimer kt(ctx, device, s, REDUX_KERNEL_DECODE);
+        if (pl.wide_table) launch_decode<uint32_t>(pl.cls, job, grid, smem, s);
+        else               launch_decode<uint16_t>(pl.cls, job, grid, smem, s);
+    }
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return REDUX_OK;
+}
+
+}  // namespace
 
 extern "C" int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *stream_, int model_kind,
                                          const redux_params_t *params, const uint8_t *d_in,
@@ -416,38 +506,9 @@ extern "C" int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *str
     CU_TRY(ctx, d->slots.reserve(n_blocks * pl.slot_stride));
     CU_TRY(ctx, d->sizes.reserve(n_blocks * sizeof(uint32_t)));
     CU_TRY(ctx, d->flag.reserve(sizeof(int32_t)));
-
-    LaneEncJob job;
-    job.in = d_in; job.in_off = d_in_offsets; job.n_blocks = n_blocks;
-    job.slots = (uint8_t *)d->slots.p; job.slot_stride = pl.slot_stride;
-    job.sizes = (uint32_t *)d->sizes.p; job.status = d_status;
-    job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
-    const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
-    const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
-    {
-        KernelTimer kt(ctx, device, s, REDUX_KERNEL_ENCODE);
-        if (pl.wide_table) launch_encode<uint32_t>(pl.cls, job, grid, smem, s);
-        else               launch_encode<uint16_t>(pl.cls, job, grid, smem, s);
-    }
-    ctx->launches++;
-    CU_TRY(ctx, cudaGetLastError());
-
-    {
-        KernelTimer kt(ctx, device, s, REDUX_KERNEL_SCAN);
-        scan_sizes_kernel<<<1, kScanThreads, 0, s>>>(job.sizes, n_blocks, d_out_offsets, out_capacity,
-                                                     (int32_t *)d->flag.p);
-    }
-    ctx->launches++;
-    CU_TRY(ctx, cudaGetLastError());
-    const uint32_t cgrid = (uint32_t)std::min<uint64_t>(n_blocks, 148 * 16);
-    {
-        KernelTimer kt(ctx, device, s, REDUX_KERNEL_COMPACT);
-        compact_kernel<<<cgrid, kCompactThreads, 0, s>>>(job.slots, pl.slot_stride, job.sizes, d_out_offsets,
-                                                         n_blocks, d_out, out_capacity, d_status);
-    }
-    ctx->launches++;
-    CU_TRY(ctx, cudaGetLastError());
-    return REDUX_OK;
+    return encode_launch(ctx, device, s, pl, magic, d_in, d_in_offsets, n_blocks, d_out, out_capacity,
+                         d_out_offsets, d_status, (uint8_t *)d->slots.p, (uint32_t *)d->sizes.p,
+                         (int32_t *)d->flag.p);
 }
 
 extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *stream_, int model_kind,
@@ -471,21 +532,8 @@ extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *str
     cudaStream_t s = (cudaStream_t)stream_;   // NULL = the default stream, as in CUDA
     const void *magic = nullptr;
     if ((rc = get_magic(ctx, d, s, pl, &magic))) return rc;
-
-    LaneDecJob job;
-    job.comp = d_comp; job.comp_off = d_comp_offsets; job.n_blocks = n_blocks;
-    job.raw = d_raw; job.raw_off = d_raw_offsets; job.raw_len = d_raw_lens; job.consumed = d_consumed;
-    job.status = d_status; job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
-    const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
-    const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
-    {
-        KernelTimer kt(ctx, device, s, REDUX_KERNEL_DECODE);
-        if (pl.wide_table) launch_decode<uint32_t>(pl.cls, job, grid, smem, s);
-        else               launch_decode<uint16_t>(pl.cls, job, grid, smem, s);
-    }
-    ctx->launches++;
-    CU_TRY(ctx, cudaGetLastError());
-    return REDUX_OK;
+    return decode_launch(ctx, device, s, pl, magic, d_comp, d_comp_offsets, n_blocks, d_raw, d_raw_offsets,
+                         d_raw_lens, d_consumed, d_status);
 }
 
 extern "C" int redux_generate_blocks_device(redux_ctx_t *ctx, int device, void *stream_, uint8_t *d_out,
@@ -508,13 +556,19 @@ extern "C" int redux_generate_blocks_device(redux_ctx_t *ctx, int device, void *
 }
 
 // ================================================================================ host-buffer API
+// End-to-end path.  A device's shard is cut into chunks of blocks; chunk k runs
+//     H2D(raw bytes, on the shared h2d stream) -> encode -> scan -> compact -> D2H(offsets, status)
+// on its own compute stream
+// so the copy engines and the SMs overlap (the coder kernels are latency-bound per lane: a chunk takes
+// about as long as the whole batch, so many chunks must be in flight together).  The host then walks the
+// chunks in order and streams each chunk's compacted bytes to its final place in the caller's buffer.
 namespace {
 
 struct Shard { uint64_t first, count; };
 
 std::vector<Shard> make_shards(uint64_t n_blocks, size_t n_dev)
 {
-    // contiguous block-index ranges, SURVEY.md 8(e)
+    // contiguous block-index ranges; same rule as redux_debug_shard
     std::vector<Shard> s(n_dev);
     for (size_t g = 0; g < n_dev; ++g) {
         uint64_t a = n_blocks * g / n_dev, b = n_blocks * (g + 1) / n_dev;
@@ -523,6 +577,26 @@ std::vector<Shard> make_shards(uint64_t n_blocks, size_t n_dev)
     return s;
 }
 
+std::vector<Shard> make_chunks(uint64_t count)
+{
+    // at most kPipeStreams chunks (one stream each), whole CTAs, at least 8 CTAs each
+    uint64_t cb = (count + kPipeStreams - 1) / kPipeStreams;
+    cb = (cb + kLaneThreads - 1) / kLaneThreads * kLaneThreads;
+    cb = std::max<uint64_t>(cb, (uint64_t)kLaneThreads * 8);
+    std::vector<Shard> c;
+    for (uint64_t a = 0; a < count; a += cb) c.push_back({a, std::min(cb, count - a)});
+    return c;
+}
+
+struct EventSet {
+    std::vector<cudaEvent_t> ev;
+    cudaError_t create(size_t n) {
+        ev.assign(n, nullptr);
+        for (auto &e : ev) { cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming); if (r != cudaSuccess) return r; }
+        return cudaSuccess;
+    }
+    ~EventSet() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+};
 
 // Runs fn(view, device_state, g) for every shard: inline for one device, one host thread per device
 // otherwise.  Each worker gets a private view of the context (own error string / launch counter) so the
@@ -551,13 +625,34 @@ void for_each_device(redux_ctx *ctx, size_t nd, std::vector<int> &rcs, F fn)
     }
 }
 
-// Phase 1 of a shard: H2D, kernels, D2H of offsets + status. Leaves the compacted bytes on the device.
-int encode_shard_phase1(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t *p,
-                        const uint8_t *in, const uint64_t *in_off, Shard sh, uint64_t out_cap_hint,
-                        uint64_t *out_off_local, int32_t *status, uint64_t *total)
+// Waits for everything this device still has in flight (used on error paths before buffers are reused).
+void drain(DeviceState *d)
 {
+    cudaStreamSynchronize(d->h2d);
+    for (int i = 0; i < kPipeStreams; ++i) cudaStreamSynchronize(d->pipe[i]);
+    cudaStreamSynchronize(d->copy);
+}
+
+// One device's shard of redux_encode_batch.
+//   stream_out != nullptr: the compacted bytes of chunk k are copied to stream_out + (bytes of the chunks
+//       before it) as soon as the chunk is done (single-device case: the shard's global base is known).
+//   stream_out == nullptr: the bytes stay on the device (st_out, chunk k at chunk_base[k]); the caller
+//       places them once the totals of the lower shards are known.
+struct EncShardOut {
+    std::vector<uint64_t> local_off;     // [count+1] shard-local offsets of the back-to-back streams
+    std::vector<uint64_t> chunk_base;    // device offset of chunk k inside st_out
+    std::vector<uint64_t> chunk_total;   // compacted bytes of chunk k
+    std::vector<Shard> chunks;
+    uint64_t total = 0;
+    bool overflow = false;               // stream_out only: capacity ran out
+};
+
+int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t *p, const uint8_t *in,
+                 const uint64_t *in_off, Shard sh, uint8_t *stream_out, uint64_t stream_cap,
+                 int32_t *status, EncShardOut *res)
+{
+    (void)kind;
     DeviceGuard g(d->device);
-    cudaStream_t s = d->stream;
     const uint64_t base = in_off[sh.first], bytes = in_off[sh.first + sh.count] - base;
     uint64_t max_len = 0;
     std::vector<uint64_t> rel(sh.count + 1);
@@ -569,25 +664,91 @@ int encode_shard_phase1(redux_ctx *ctx, DeviceState *d, int kind, const redux_pa
     Plan pl;
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
-    uint64_t worst = 0;
-    for (uint64_t i = 0; i < sh.count; ++i) worst += redux_compress_bound(rel[i + 1] - rel[i], pl.c);
-    const uint64_t dcap = std::min(worst, out_cap_hint);
+    res->chunks = make_chunks(sh.count);
+    const size_t nc = res->chunks.size();
+    res->chunk_base.assign(nc, 0); res->chunk_total.assign(nc, 0);
+    res->local_off.assign(sh.count + 1, 0);
+    std::vector<uint64_t> chunk_cap(nc);
+    uint64_t dcap = 0;
+    for (size_t k = 0; k < nc; ++k) {
+        uint64_t w = 0;
+        for (uint64_t i = 0; i < res->chunks[k].count; ++i) {
+            const uint64_t b = res->chunks[k].first + i;
+            w += redux_compress_bound(rel[b + 1] - rel[b], pl.c);
+        }
+        chunk_cap[k] = w;
+        res->chunk_base[k] = dcap;
+        dcap += (w + 15) & ~(uint64_t)15;
+    }
     CU_TRY(ctx, d->st_in.reserve(bytes + 32));
     CU_TRY(ctx, d->st_off.reserve((sh.count + 1) * sizeof(uint64_t)));
     CU_TRY(ctx, d->st_out.reserve(dcap + 32));
-    CU_TRY(ctx, d->st_ooff.reserve((sh.count + 1) * sizeof(uint64_t)));
+    CU_TRY(ctx, d->st_ooff.reserve((sh.count + nc) * sizeof(uint64_t)));
     CU_TRY(ctx, d->st_status.reserve(sh.count * sizeof(int32_t)));
-    CU_TRY(ctx, cudaMemcpyAsync(d->st_in.p, in + base, bytes, cudaMemcpyHostToDevice, s));
-    CU_TRY(ctx, cudaMemcpyAsync(d->st_off.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    CU_TRY(ctx, cudaStreamSynchronize(s));   // rel is a stack-lifetime vector
-    rc = redux_encode_batch_device(ctx, d->device, s, kind, p, (const uint8_t *)d->st_in.p,
-                                   (const uint64_t *)d->st_off.p, sh.count, max_len, (uint8_t *)d->st_out.p,
-                                   dcap, (uint64_t *)d->st_ooff.p, (int32_t *)d->st_status.p);
-    if (rc) return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(out_off_local, d->st_ooff.p, (sh.count + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CU_TRY(ctx, cudaMemcpyAsync(status, d->st_status.p, sh.count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    CU_TRY(ctx, cudaStreamSynchronize(s));
-    *total = out_off_local[sh.count];
+    CU_TRY(ctx, d->slots.reserve(sh.count * pl.slot_stride));
+    CU_TRY(ctx, d->sizes.reserve(sh.count * sizeof(uint32_t)));
+    CU_TRY(ctx, d->flag.reserve(nc * sizeof(int32_t)));
+    CU_TRY(ctx, d->pin_off.reserve((sh.count + nc) * sizeof(uint64_t)));
+    CU_TRY(ctx, d->pin_status.reserve(sh.count * sizeof(int32_t)));
+    const void *magic = nullptr;
+    if ((rc = get_magic(ctx, d, d->h2d, pl, &magic))) return rc;
+    EventSet evs;                       // [0, nc): chunk done; [nc, 2nc): chunk input on the device
+    CU_TRY(ctx, evs.create(2 * nc));
+    CU_TRY(ctx, cudaMemcpyAsync(d->st_off.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d->h2d));
+
+    uint8_t *d_in = (uint8_t *)d->st_in.p, *d_out = (uint8_t *)d->st_out.p;
+    uint64_t *d_off = (uint64_t *)d->st_off.p, *d_ooff = (uint64_t *)d->st_ooff.p;
+    int32_t *d_status = (int32_t *)d->st_status.p;
+    uint64_t *h_ooff = (uint64_t *)d->pin_off.p;
+    int32_t *h_status = (int32_t *)d->pin_status.p;
+    for (size_t k = 0; k < nc; ++k) {
+        const Shard c = res->chunks[k];
+        cudaStream_t s = d->pipe[k % kPipeStreams];
+        rc = REDUX_OK;
+        cudaError_t e = cudaSuccess;
+        const uint64_t b0 = rel[c.first], b1 = rel[c.first + c.count];
+        if (b1 > b0) e = cudaMemcpyAsync(d_in + b0, in + base + b0, b1 - b0, cudaMemcpyHostToDevice, d->h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(evs.ev[nc + k], d->h2d);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[nc + k], 0);
+        if (e == cudaSuccess)
+            rc = encode_launch(ctx, d->device, s, pl, magic, d_in, d_off + c.first, c.count,
+                               d_out + res->chunk_base[k], chunk_cap[k], d_ooff + c.first + k,
+                               d_status + c.first, (uint8_t *)d->slots.p + c.first * pl.slot_stride,
+                               (uint32_t *)d->sizes.p + c.first, (int32_t *)d->flag.p + k);
+        if (e == cudaSuccess && rc == REDUX_OK)
+            e = cudaMemcpyAsync(h_ooff + c.first + k, d_ooff + c.first + k, (c.count + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && rc == REDUX_OK)
+            e = cudaMemcpyAsync(h_status + c.first, d_status + c.first, c.count * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && rc == REDUX_OK) e = cudaEventRecord(evs.ev[k], s);
+        if (e != cudaSuccess || rc != REDUX_OK) {
+            drain(d);
+            if (rc != REDUX_OK) return rc;
+            (void)cudaGetLastError();
+            return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline enqueue", e);
+        }
+    }
+    // in order: offsets of chunk k become shard-local offsets; its bytes go out while later chunks run
+    uint64_t pos = 0;
+    for (size_t k = 0; k < nc; ++k) {
+        const Shard c = res->chunks[k];
+        cudaError_t e = cudaEventSynchronize(evs.ev[k]);
+        if (e != cudaSuccess) { drain(d); (void)cudaGetLastError(); return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline", e); }
+        const uint64_t *lo = h_ooff + c.first + k;
+        for (uint64_t i = 0; i <= c.count; ++i) res->local_off[c.first + i] = pos + lo[i];
+        std::memcpy(status + c.first, h_status + c.first, c.count * sizeof(int32_t));
+        res->chunk_total[k] = lo[c.count];
+        if (stream_out && !res->overflow) {
+            uint64_t nbytes = lo[c.count];
+            if (pos + nbytes > stream_cap) { res->overflow = true; nbytes = stream_cap - pos; }   // the prefix that fits
+            if (nbytes) {
+                e = cudaMemcpyAsync(stream_out + pos, d_out + res->chunk_base[k], nbytes, cudaMemcpyDeviceToHost, d->copy);
+                if (e != cudaSuccess) { drain(d); (void)cudaGetLastError(); return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline D2H", e); }
+            }
+        }
+        pos += lo[c.count];
+    }
+    res->total = pos;
+    CU_TRY(ctx, cudaStreamSynchronize(d->copy));
     return REDUX_OK;
 }
 
@@ -608,40 +769,43 @@ extern "C" int redux_encode_batch(redux_ctx_t *ctx, int model_kind, const redux_
 
     const size_t nd = std::min<uint64_t>(ctx->devs.size(), n_blocks);
     std::vector<Shard> shards = make_shards(n_blocks, nd);
-    std::vector<std::vector<uint64_t>> local(nd);
-    std::vector<uint64_t> totals(nd, 0);
+    std::vector<EncShardOut> res(nd);
     std::vector<int> rcs(nd, REDUX_OK);
-    for (size_t g = 0; g < nd; ++g) local[g].resize(shards[g].count + 1);
     for_each_device(ctx, nd, rcs, [&](redux_ctx *view, DeviceState *d, size_t g) {
-        return encode_shard_phase1(view, d, model_kind, params, in, in_offsets, shards[g], out_capacity,
-                                   local[g].data(), status + shards[g].first, &totals[g]);
+        return encode_shard(view, d, model_kind, params, in, in_offsets, shards[g],
+                            nd == 1 ? out : nullptr, out_capacity, status + shards[g].first, &res[g]);
     });
     for (size_t g = 0; g < nd; ++g) if (rcs[g]) return rcs[g];
 
-    // global offsets, then phase 2: D2H of each shard's bytes to its place
+    // global offsets; with several devices the bytes are placed now that every shard's base is known
     uint64_t base = 0;
     std::vector<uint64_t> bases(nd);
     for (size_t g = 0; g < nd; ++g) {
         bases[g] = base;
-        for (uint64_t i = 0; i <= shards[g].count; ++i) out_offsets[shards[g].first + i] = base + local[g][i];
-        base += totals[g];
+        for (uint64_t i = 0; i <= shards[g].count; ++i) out_offsets[shards[g].first + i] = base + res[g].local_off[i];
+        base += res[g].total;
     }
     if (base > out_capacity) {
-        // streams that do not fit were not compacted (status 6 where the device saw it); a shard whose
-        // global placement overflows is reported here
-        for (size_t g = 0; g < nd; ++g)
-            for (uint64_t i = 0; i < shards[g].count; ++i)
-                if (out_offsets[shards[g].first + i + 1] > out_capacity) status[shards[g].first + i] = REDUX_OUT_CAPACITY;
+        for (uint64_t i = 0; i < n_blocks; ++i)
+            if (out_offsets[i + 1] > out_capacity) status[i] = REDUX_OUT_CAPACITY;
         return fail(ctx, REDUX_OUT_CAPACITY, "output buffer too small for the compressed batch");
     }
-    for (size_t g = 0; g < nd; ++g) {
-        DeviceState &d = ctx->devs[g];
-        DeviceGuard gd(d.device);
-        if (totals[g]) CU_TRY(ctx, cudaMemcpyAsync(out + bases[g], d.st_out.p, totals[g], cudaMemcpyDeviceToHost, d.stream));
-    }
-    for (size_t g = 0; g < nd; ++g) {
-        DeviceGuard gd(ctx->devs[g].device);
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->devs[g].stream));
+    if (nd > 1) {
+        for (size_t g = 0; g < nd; ++g) {
+            DeviceState &d = ctx->devs[g];
+            DeviceGuard gd(d.device);
+            uint64_t pos = bases[g];
+            for (size_t k = 0; k < res[g].chunks.size(); ++k) {
+                if (res[g].chunk_total[k])
+                    CU_TRY(ctx, cudaMemcpyAsync(out + pos, (const uint8_t *)d.st_out.p + res[g].chunk_base[k],
+                                                res[g].chunk_total[k], cudaMemcpyDeviceToHost, d.copy));
+                pos += res[g].chunk_total[k];
+            }
+        }
+        for (size_t g = 0; g < nd; ++g) {
+            DeviceGuard gd(ctx->devs[g].device);
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->devs[g].copy));
+        }
     }
     for (uint64_t i = 0; i < n_blocks; ++i) if (status[i]) return status[i];
     return REDUX_OK;
@@ -649,15 +813,19 @@ extern "C" int redux_encode_batch(redux_ctx_t *ctx, int model_kind, const redux_
 
 namespace {
 
+// One device's shard of redux_decode_batch: chunk k runs
+//     H2D(compressed bytes) -> decode -> D2H(decoded slots) -> D2H(lengths, consumed, status)
+// (H2D on the shared h2d stream, the rest on the chunk's own stream); nothing depends on another chunk or shard.
 int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t *p, const uint8_t *comp,
                  const uint64_t *comp_off, Shard sh, uint8_t *raw, const uint64_t *raw_off,
                  uint64_t *raw_lens, uint64_t *consumed, int32_t *status)
 {
+    (void)kind;
     DeviceGuard g(d->device);
-    cudaStream_t s = d->stream;
     const uint64_t cbase = comp_off[sh.first], cbytes = comp_off[sh.first + sh.count] - cbase;
     const uint64_t rbase = raw_off[sh.first], rbytes = raw_off[sh.first + sh.count] - rbase;
-    std::vector<uint64_t> crel(sh.count + 1), rrel(sh.count + 1);
+    std::vector<uint64_t> rel(2 * (sh.count + 1));            // [crel | rrel]
+    uint64_t *crel = rel.data(), *rrel = rel.data() + sh.count + 1;
     uint64_t max_len = 0;
     for (uint64_t i = 0; i <= sh.count; ++i) {
         crel[i] = comp_off[sh.first + i] - cbase;
@@ -667,39 +835,64 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
             max_len = std::max(max_len, rrel[i] - rrel[i - 1]);
         }
     }
+    Plan pl;
+    int rc = make_plan(ctx, p, max_len, &pl);
+    if (rc) return rc;
+    const std::vector<Shard> chunks = make_chunks(sh.count);
+    const size_t nc = chunks.size();
     CU_TRY(ctx, d->st_in.reserve(cbytes + 32));
-    CU_TRY(ctx, d->st_off.reserve((sh.count + 1) * sizeof(uint64_t)));
-    CU_TRY(ctx, d->st_roff.reserve((sh.count + 1) * sizeof(uint64_t)));
+    CU_TRY(ctx, d->st_off.reserve(rel.size() * sizeof(uint64_t)));
     CU_TRY(ctx, d->st_out.reserve(rbytes + 32));
     CU_TRY(ctx, d->st_aux0.reserve(sh.count * sizeof(uint64_t)));
     CU_TRY(ctx, d->st_aux1.reserve(sh.count * sizeof(uint64_t)));
     CU_TRY(ctx, d->st_status.reserve(sh.count * sizeof(int32_t)));
-    CU_TRY(ctx, cudaMemcpyAsync(d->st_in.p, comp + cbase, cbytes, cudaMemcpyHostToDevice, s));
-    CU_TRY(ctx, cudaMemcpyAsync(d->st_off.p, crel.data(), crel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    CU_TRY(ctx, cudaMemcpyAsync(d->st_roff.p, rrel.data(), rrel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
-    CU_TRY(ctx, cudaStreamSynchronize(s));
-    int rc = redux_decode_batch_device(ctx, d->device, s, kind, p, (const uint8_t *)d->st_in.p,
-                                       (const uint64_t *)d->st_off.p, sh.count, max_len, (uint8_t *)d->st_out.p,
-                                       (const uint64_t *)d->st_roff.p, (uint64_t *)d->st_aux0.p,
-                                       (uint64_t *)d->st_aux1.p, (int32_t *)d->st_status.p);
-    if (rc) return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(raw_lens + sh.first, d->st_aux0.p, sh.count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CU_TRY(ctx, cudaMemcpyAsync(consumed + sh.first, d->st_aux1.p, sh.count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    CU_TRY(ctx, cudaMemcpyAsync(status + sh.first, d->st_status.p, sh.count * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    CU_TRY(ctx, cudaStreamSynchronize(s));
-    // copy back only what was decoded: contiguous when every slot is full (the usual case), else per block
-    bool full = true;
-    for (uint64_t i = 0; i < sh.count && full; ++i) full = raw_lens[sh.first + i] == rrel[i + 1] - rrel[i];
-    if (full) {
-        if (rbytes) CU_TRY(ctx, cudaMemcpyAsync(raw + rbase, d->st_out.p, rbytes, cudaMemcpyDeviceToHost, s));
-    } else {
-        for (uint64_t i = 0; i < sh.count; ++i) {
-            const uint64_t n = raw_lens[sh.first + i];
-            if (n) CU_TRY(ctx, cudaMemcpyAsync(raw + rbase + rrel[i], (const uint8_t *)d->st_out.p + rrel[i], n,
-                                               cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, d->pin_aux0.reserve(sh.count * sizeof(uint64_t)));
+    CU_TRY(ctx, d->pin_aux1.reserve(sh.count * sizeof(uint64_t)));
+    CU_TRY(ctx, d->pin_status.reserve(sh.count * sizeof(int32_t)));
+    const void *magic = nullptr;
+    if ((rc = get_magic(ctx, d, d->pipe[0], pl, &magic))) return rc;
+    EventSet evs;                       // chunk input on the device
+    CU_TRY(ctx, evs.create(nc));
+    CU_TRY(ctx, cudaMemcpyAsync(d->st_off.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d->h2d));
+    uint8_t *d_comp = (uint8_t *)d->st_in.p, *d_raw = (uint8_t *)d->st_out.p;
+    uint64_t *d_coff = (uint64_t *)d->st_off.p, *d_roff = d_coff + sh.count + 1;
+    uint64_t *d_len = (uint64_t *)d->st_aux0.p, *d_cons = (uint64_t *)d->st_aux1.p;
+    int32_t *d_status = (int32_t *)d->st_status.p;
+    uint64_t *h_len = (uint64_t *)d->pin_aux0.p, *h_cons = (uint64_t *)d->pin_aux1.p;
+    int32_t *h_status = (int32_t *)d->pin_status.p;
+    for (size_t k = 0; k < nc; ++k) {
+        const Shard c = chunks[k];
+        cudaStream_t s = d->pipe[k % kPipeStreams];
+        rc = REDUX_OK;
+        cudaError_t e = cudaSuccess;
+        const uint64_t c0 = crel[c.first], c1 = crel[c.first + c.count];
+        const uint64_t r0 = rrel[c.first], r1 = rrel[c.first + c.count];
+        if (c1 > c0) e = cudaMemcpyAsync(d_comp + c0, comp + cbase + c0, c1 - c0, cudaMemcpyHostToDevice, d->h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(evs.ev[k], d->h2d);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[k], 0);
+        if (e == cudaSuccess)
+            rc = decode_launch(ctx, d->device, s, pl, magic, d_comp, d_coff + c.first, c.count, d_raw,
+                               d_roff + c.first, d_len + c.first, d_cons + c.first, d_status + c.first);
+        // the whole slot range of the chunk goes back; bytes beyond raw_lens[i] inside a slot are unspecified
+        if (e == cudaSuccess && rc == REDUX_OK && r1 > r0)
+            e = cudaMemcpyAsync(raw + rbase + r0, d_raw + r0, r1 - r0, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && rc == REDUX_OK)
+            e = cudaMemcpyAsync(h_len + c.first, d_len + c.first, c.count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && rc == REDUX_OK)
+            e = cudaMemcpyAsync(h_cons + c.first, d_cons + c.first, c.count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && rc == REDUX_OK)
+            e = cudaMemcpyAsync(h_status + c.first, d_status + c.first, c.count * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess || rc != REDUX_OK) {
+            drain(d);
+            if (rc != REDUX_OK) return rc;
+            (void)cudaGetLastError();
+            return fail(ctx, REDUX_CUDA_ERROR, "decode pipeline enqueue", e);
         }
     }
-    CU_TRY(ctx, cudaStreamSynchronize(s));
+    for (int i = 0; i < kPipeStreams; ++i) CU_TRY(ctx, cudaStreamSynchronize(d->pipe[i]));
+    std::memcpy(raw_lens + sh.first, h_len, sh.count * sizeof(uint64_t));
+    std::memcpy(consumed + sh.first, h_cons, sh.count * sizeof(uint64_t));
+    std::memcpy(status + sh.first, h_status, sh.count * sizeof(int32_t));
     return REDUX_OK;
 }
 
