@@ -131,6 +131,9 @@ int redux_decode_batch(redux_ctx_t *ctx, int model_kind, const redux_params_t *p
  * `device`, which must be one of the context's devices; work is enqueued on `stream` (a
  * cudaStream_t; NULL = the CUDA default stream) and is asynchronous).
  * max_block_len: an upper bound of every block's raw length (sizes the per-block output slots).
+ * Alignment contract: the kernels read d_in / d_comp with aligned 16-byte / 4-byte vector loads, so the
+ * bytes from the enclosing 16-byte boundaries of the first and last byte of each stream must be readable
+ * (true for any cudaMalloc / torch allocation: granularity >= 256 B); values outside a stream are ignored.
  * total_in_bytes = in_offsets[n_blocks] as known by the host. */
 int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *stream, int model_kind,
                               const redux_params_t *params,

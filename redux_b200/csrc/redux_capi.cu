@@ -17,6 +17,7 @@
 #include "redux_batch_kernels.cuh"
 #include "redux_common.cuh"
 #include "redux_lane_codec.cuh"
+#include "redux_warp_codec.cuh"
 
 using namespace rdx;
 
@@ -129,7 +130,21 @@ cudaError_t configure_kernels()
 // Shape of one launch derived from the parameters and the longest block.
 struct Plan {
     int cls; uint32_t f, c, tcap; bool wide_table; uint32_t magic_len; uint64_t slot_stride;
+    bool warp = false;      // one stream per warp (latency mapping) instead of one per lane
 };
+
+// REDUX_SCHED_AUTO: with this few streams both mappings are bound by the serial latency of the longest
+// stream; measured on B200 (scripts/bench_small.py, profiles/r01_small_batches.json) the cooperating
+// warp decodes 1.3-1.45x faster and encodes within -10%..+15% of a lone lane.  Above it, 32 streams per
+// warp win on issue slots.
+constexpr uint64_t kWarpAutoMaxBlocks = 512;
+
+bool choose_warp(const redux_ctx *ctx, uint64_t n_blocks)
+{
+    if (ctx->sched == REDUX_SCHED_WARP) return true;
+    if (ctx->sched == REDUX_SCHED_LANE) return false;
+    return n_blocks < kWarpAutoMaxBlocks;
+}
 
 int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, Plan *pl)
 {
@@ -188,6 +203,21 @@ void launch_decode(int cls, const LaneDecJob &job, uint32_t grid, size_t smem, c
     if (cls == kNarrow)    decode_lane_kernel<TW, kNarrow><<<grid, kLaneThreads, smem, s>>>(job);
     else if (cls == kWide) decode_lane_kernel<TW, kWide><<<grid, kLaneThreads, smem, s>>>(job);
     else                   decode_lane_kernel<TW, kHuge><<<grid, kLaneThreads, smem, s>>>(job);
+}
+
+void launch_encode_warp(int cls, const LaneEncJob &job, cudaStream_t s)
+{
+    const uint32_t grid = (uint32_t)((job.n_blocks + kWarpCtaWarps - 1) / kWarpCtaWarps);
+    if (cls == kNarrow)    encode_warp_kernel<kNarrow><<<grid, kWarpCtaThreads, 0, s>>>(job);
+    else if (cls == kWide) encode_warp_kernel<kWide><<<grid, kWarpCtaThreads, 0, s>>>(job);
+    else                   encode_warp_kernel<kHuge><<<grid, kWarpCtaThreads, 0, s>>>(job);
+}
+void launch_decode_warp(int cls, const LaneDecJob &job, cudaStream_t s)
+{
+    const uint32_t grid = (uint32_t)((job.n_blocks + kWarpCtaWarps - 1) / kWarpCtaWarps);
+    if (cls == kNarrow)    decode_warp_kernel<kNarrow><<<grid, kWarpCtaThreads, 0, s>>>(job);
+    else if (cls == kWide) decode_warp_kernel<kWide><<<grid, kWarpCtaThreads, 0, s>>>(job);
+    else                   decode_warp_kernel<kHuge><<<grid, kWarpCtaThreads, 0, s>>>(job);
 }
 
 int check_kind(redux_ctx *ctx, int kind)
@@ -402,8 +432,7 @@ extern "C" int redux_ctx_timing_collect(redux_ctx_t *ctx, double *ms, uint64_t *
 extern "C" int redux_ctx_set_schedule(redux_ctx_t *ctx, int sched)
 {
     if (!ctx) return REDUX_INVALID_INPUT;
-    if (sched == REDUX_SCHED_AUTO || sched == REDUX_SCHED_LANE) { ctx->sched = sched; return REDUX_OK; }
-    if (sched == REDUX_SCHED_WARP) return fail(ctx, REDUX_UNSUPPORTED, "warp schedule not built yet");
+    if (sched == REDUX_SCHED_AUTO || sched == REDUX_SCHED_LANE || sched == REDUX_SCHED_WARP) { ctx->sched = sched; return REDUX_OK; }
     return fail(ctx, REDUX_INVALID_INPUT, "unknown schedule");
 }
 
@@ -436,8 +465,9 @@ int encode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
     {
         KernelTimer kt(ctx, device, s, REDUX_KERNEL_ENCODE);
-        if (pl.wide_table) launch_encode<uint32_t>(pl.cls, job, grid, smem, s);
-        else               launch_encode<uint16_t>(pl.cls, job, grid, smem, s);
+        if (pl.warp)            launch_encode_warp(pl.cls, job, s);
+        else if (pl.wide_table) launch_encode<uint32_t>(pl.cls, job, grid, smem, s);
+        else                    launch_encode<uint16_t>(pl.cls, job, grid, smem, s);
     }
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
@@ -471,8 +501,9 @@ int decode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
     {
         KernelTimer kt(ctx, device, s, REDUX_KERNEL_DECODE);
-        if (pl.wide_table) launch_decode<uint32_t>(pl.cls, job, grid, smem, s);
-        else               launch_decode<uint16_t>(pl.cls, job, grid, smem, s);
+        if (pl.warp)            launch_decode_warp(pl.cls, job, s);
+        else if (pl.wide_table) launch_decode<uint32_t>(pl.cls, job, grid, smem, s);
+        else                    launch_decode<uint16_t>(pl.cls, job, grid, smem, s);
     }
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
@@ -492,6 +523,7 @@ extern "C" int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *str
     if ((rc = check_kind(ctx, model_kind))) return rc;
     Plan pl;
     if ((rc = make_plan(ctx, params, max_block_len, &pl))) return rc;
+    pl.warp = choose_warp(ctx, n_blocks);
     DeviceState *d = find_dev(ctx, device);
     if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
     if (!d_in_offsets || !d_out_offsets || !d_status || (!d_out && out_capacity))
@@ -523,6 +555,7 @@ extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *str
     if ((rc = check_kind(ctx, model_kind))) return rc;
     Plan pl;
     if ((rc = make_plan(ctx, params, max_block_len, &pl))) return rc;
+    pl.warp = choose_warp(ctx, n_blocks);
     DeviceState *d = find_dev(ctx, device);
     if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
     if (n_blocks == 0) return REDUX_OK;
@@ -664,6 +697,7 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     Plan pl;
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
+    pl.warp = choose_warp(ctx, sh.count);
     res->chunks = make_chunks(sh.count);
     const size_t nc = res->chunks.size();
     res->chunk_base.assign(nc, 0); res->chunk_total.assign(nc, 0);
@@ -838,6 +872,7 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     Plan pl;
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
+    pl.warp = choose_warp(ctx, sh.count);
     const std::vector<Shard> chunks = make_chunks(sh.count);
     const size_t nc = chunks.size();
     CU_TRY(ctx, d->st_in.reserve(cbytes + 32));

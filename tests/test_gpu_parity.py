@@ -17,9 +17,12 @@ TRIPLES = [(8, 14, 16), (8, 22, 24), (8, 30, 32)]          # tests/corpora.rs:35
 KINDS = [(rb.AdaptiveLinearModel, o.LINEAR), (rb.AdaptiveTreeModel, o.TREE)]
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["lane", "warp"])
+def ctx(request):
+    """Every parity test runs on both stream-to-thread mappings: one stream per lane (Fenwick table in
+    shared memory) and one stream per warp (cumulative array in registers)."""
     c = rb.Context()
+    c.set_schedule(rb.SCHED_LANE if request.param == "lane" else rb.SCHED_WARP)
     yield c
     c.close()
 
@@ -88,6 +91,25 @@ def test_kat_vectors_single_stream(ctx):
             assert (ic, oc) == (len(data), len(want))
             dec, (ic2, oc2) = ctx.decompress(out, cls(rb.Parameters(*p)), len(data) + 8)
             assert dec == data and (ic2, oc2) == (len(want), len(data))
+
+
+def test_auto_schedule_gives_the_same_bytes():
+    """REDUX_SCHED_AUTO picks the warp mapping for small batches and the lane mapping for large ones;
+    the bytes never depend on the mapping."""
+    n, L = 2600, 1500
+    raw = rb.generate_blocks_host(0, n, L, SEED)
+    off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+    model = rb.AdaptiveLinearModel(rb.Parameters(8, 22, 24))
+    outs = []
+    for sched, count in ((rb.SCHED_AUTO, n), (rb.SCHED_AUTO, 100), (rb.SCHED_LANE, n), (rb.SCHED_WARP, n)):
+        with rb.Context() as c:
+            c.set_schedule(sched)
+            comp, coff, st = c.encode_batch(raw[:count * L], off[:count + 1], model)
+            back, lens, cons, st = c.decode_batch(comp, coff, off[:count + 1], model)
+            assert (back == raw[:count * L]).all()
+            outs.append((comp.tobytes(), coff.tobytes()))
+    assert outs[0] == outs[2] == outs[3]
+    assert outs[2][0].startswith(outs[1][0])
 
 
 def test_dropin_compress_decompress_doctest():
