@@ -136,18 +136,52 @@ struct LaneTable {
     }
 
     // update(s+1) of adaptive_tree.rs:83-92 minus the two unstored nodes: node s+1, then for every
-    // clear bit k-1 of s the node (s | (2^k-1)) + 1, while below 256.
+    // clear bit k-1 of s the node (s | (2^k-1)) + 1, while below 256.  The surviving levels are exactly
+    // the set bits of ~s below its highest one (the highest clear bit of s leads to node 256).
     __device__ __forceinline__ void update(uint32_t s) {
         const uint32_t S = s << 5;
-        if (s != 255u) {
+        const uint32_t q = ~s & 255u;
+        const uint32_t levels = q ? (q ^ (1u << (31 - clz32(q)))) : 0u;
+        if (q) {                                                        // s != 255
             const uint32_t i0 = (s & 1u) ? S + 32u : (uint32_t)((int)S + 32 + kOddAdj);
             t[i0] = (TW)(t[i0] + 1);
         }
 #pragma unroll
         for (int k = 1; k < 8; ++k) {
-            const uint32_t base = S | (((1u << k) - 1u) << 5);           // (s | mask_k) * 32
-            if (!(s & (1u << (k - 1))) && base < (255u << 5))
-                t[base + 32u] = (TW)(t[base + 32u] + 1);
+            if (levels & (1u << (k - 1))) {
+                const uint32_t i = (S | (((1u << k) - 1u) << 5)) + 32u;   // ((s | mask_k) + 1) * 32, an even node
+                t[i] = (TW)(t[i] + 1);
+            }
+        }
+    }
+
+    // index (in TW units from t) of node n, either parity
+    static __device__ __forceinline__ int node_index(uint32_t n) { return (int)(n << 5) + ((n & 1u) ? kOddAdj : 0); }
+
+    // Once the model is frozen (adaptive_tree.rs:84) the tree is read-only: rewrite it in place as the
+    // plain cumulative array C[i] = cum(i) - i (the layout of AdaptiveLinearModel, adaptive_linear.rs:26-28),
+    // so that a lookup is two loads.  Descending i only reads nodes <= i, which are still Fenwick nodes.
+    __device__ __forceinline__ void freeze_to_cumulative() {
+        for (uint32_t i = 255; i >= 1; --i) {
+            uint32_t sum = 0;
+            for (uint32_t x = i; x; x &= x - 1) sum += t[node_index(x)];
+            t[node_index(i)] = (TW)sum;
+        }
+    }
+    // (cum(s), cum(s+1)) from the cumulative array; total = count
+    __device__ __forceinline__ void query_frozen(uint32_t s, uint32_t count, uint32_t &cl, uint32_t &ch) const {
+        if (sizeof(TW) == 2) {
+            // node pairs (2m, 2m+1) share word m: one or two aligned 32-bit loads
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(t);
+            const uint32_t w0 = w[(s >> 1) << 5], w1 = w[(((s + 1) >> 1) & 127u) << 5];
+            const bool odd = s & 1u;
+            cl = s + (odd ? (w0 >> 16) : (w0 & 0xFFFFu));
+            const uint32_t hi = odd ? (w1 & 0xFFFFu) : (w0 >> 16);
+            ch = (s == 255u) ? count - 1 : s + 1 + hi;
+        } else {
+            cl = s + t[s << 5];
+            const uint32_t hi = t[((s + 1) & 255u) << 5];
+            ch = (s == 255u) ? count - 1 : s + 1 + hi;
         }
     }
 };
@@ -315,11 +349,14 @@ encode_lane_kernel(const LaneEncJob job)
     const uint32_t tt = n_adapt;                          // updates done = min(len, tcap)
     const M gf = gn;                                      // = magic[tt]
     const uint32_t countf = kNsym + tt;
-    for (; t < len; ++t) {
-        const uint32_t sym = src.next();
-        uint32_t cl, ch;
-        tab.query(sym, tt, cl, ch);
-        encode_step<CLS>(low, high, pend, sink, cl, ch, countf, gf, c);
+    if (t < len) {
+        tab.freeze_to_cumulative();
+        for (; t < len; ++t) {
+            const uint32_t sym = src.next();
+            uint32_t cl, ch;
+            tab.query_frozen(sym, countf, cl, ch);
+            encode_step<CLS>(low, high, pend, sink, cl, ch, countf, gf, c);
+        }
     }
     // EOF symbol: cum(256) = total - 1 (EOF's own frequency never grows), then the tail of
     // src/codec.rs:91-99: the remaining `extra` MSBs of low, then flush.
