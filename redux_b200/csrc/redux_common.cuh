@@ -121,31 +121,34 @@ RDX_HD int clz64(uint64_t x) {
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct Renorm { T low, high; uint32_t n1, k; };
 
+// Shifts that give 0 once the amount reaches the register width (the degenerate low == high case
+// shifts a 32-bit register by 32).
+RDX_HD uint32_t shl_sat(uint32_t x, uint32_t n) { return (uint32_t)((uint64_t)x << n); }              // n <= 63
+RDX_HD uint64_t shl_sat(uint64_t x, uint32_t n) { return n >= 64 ? 0 : x << n; }
+RDX_HD uint32_t ones_sat(uint32_t, uint32_t n) { return (uint32_t)(((uint64_t)1 << n) - 1); }          // n <= 63
+RDX_HD uint64_t ones_sat(uint64_t, uint32_t n) { return n >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << n) - 1); }
+
 template <typename T>
 RDX_HD Renorm<T> renorm(T low, T high, uint32_t c) {
     constexpr int W = sizeof(T) * 8;
     const T maxv = (c == (uint32_t)W) ? ~(T)0 : ((((T)1) << c) - 1);
-    T x = low ^ high;
-    int lz = (W == 32) ? clz32((uint32_t)x) : clz64((uint64_t)x);
-    uint32_t n1 = (uint32_t)lz - (uint32_t)(W - c);           // x == 0 -> lz == W -> n1 == c
-    // shift out the n1 common bits; high refills with ones (src/codec.rs:87-88)
-    T l1, h1;
-    if (n1 >= (uint32_t)W) { l1 = 0; h1 = maxv; }
-    else {
-        l1 = (T)(low << n1) & maxv;
-        h1 = (T)((high << n1) | ((((T)1) << n1) - 1)) & maxv;
-    }
-    // E3 run: bits c-2 downwards with low=1, high=0
-    T z = (T)(l1 & ~h1) << (W + 1 - c);                       // bit c-2 -> bit W-1; low bits zero
-    T nz = ~z;                                                // has a 1 in its low (W+1-c) >= 1 bits
-    uint32_t k = (uint32_t)((W == 32) ? clz32((uint32_t)nz) : clz64((uint64_t)nz));
     const T body = maxv >> 1;                                 // bits below the MSB
     const T half = body + 1;
+    const T x = low ^ high;
+    const int lz = (W == 32) ? clz32((uint32_t)x) : clz64((uint64_t)x);
+    const uint32_t n1 = (uint32_t)lz - (uint32_t)(W - c);     // x == 0 -> lz == W -> n1 == c
+    // E3 run: after the n1 shifts, positions c-2 downwards with low=1, high=0.  Shifting (low & ~high)
+    // left by n1 + (W+1-c) puts position c-2 of the shifted registers at bit W-1 and drops everything above.
+    const T z = shl_sat((T)(low & ~high), n1 + (uint32_t)(W + 1 - c));
+    const T nz = ~z;                                          // low (W+1-c) >= 1 bits are ones: clz <= c-1
+    const uint32_t k = (uint32_t)((W == 32) ? clz32((uint32_t)nz) : clz64((uint64_t)nz));
+    const uint32_t n = n1 + k;                                // total shifts, <= c
     Renorm<T> r;
     r.n1 = n1; r.k = k;
-    r.low = (T)(l1 << k) & body;                              // MSB of low stays 0
-    r.high = ((T)((h1 << k) | ((((T)1) << k) - 1)) & body) | half;   // MSB of high stays 1
-    if (n1 == c) { r.low = 0; r.high = maxv; }                // degenerate low==high: k == 0 already
+    // both stages at once: shift by n, high refills with ones; MSB of low is 0, of high is 1 (src/codec.rs:87-88
+    // after the E3 subtraction of :77-78)
+    r.low = shl_sat(low, n) & body;
+    r.high = ((shl_sat(high, n) | ones_sat((T)0, n)) & body) | half;
     return r;
 }
 
