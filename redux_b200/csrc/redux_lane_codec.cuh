@@ -351,12 +351,17 @@ encode_lane_kernel(const LaneEncJob job)
     const uint32_t countf = kNsym + tt;
     if (t < len) {
         tab.freeze_to_cumulative();
-        for (; t < len; ++t) {
-            const uint32_t sym = src.next();
-            uint32_t cl, ch;
-            tab.query_frozen(sym, countf, cl, ch);
-            encode_step<CLS>(low, high, pend, sink, cl, ch, countf, gf, c);
+        // The lookup does not depend on the coder state: fetch + look up symbol t+1 before
+        // coding symbol t, so the shared-memory latency overlaps the range update of the previous symbol.
+        uint32_t cl, ch;
+        tab.query_frozen(src.next(), countf, cl, ch);
+        for (; t + 1 < len; ++t) {
+            const uint32_t cl_cur = cl, ch_cur = ch;
+            tab.query_frozen(src.next(), countf, cl, ch);
+            encode_step<CLS>(low, high, pend, sink, cl_cur, ch_cur, countf, gf, c);
         }
+        encode_step<CLS>(low, high, pend, sink, cl, ch, countf, gf, c);
+        ++t;
     }
     // EOF symbol: cum(256) = total - 1 (EOF's own frequency never grows), then the tail of
     // src/codec.rs:91-99: the remaining `extra` MSBs of low, then flush.
