@@ -31,6 +31,9 @@ def run(ctx, sched, data, off, model, reps=3):
     assert (back == data).all()
     return te, td, comp, coff
 
+SWEEP = [(8, 10, 16), (8, 14, 16), (8, 16, 18), (8, 20, 22), (8, 22, 24), (8, 24, 30), (8, 30, 32)]   # config 5
+
+
 def main():
     ctx = rb.Context([0])
     res = {}
@@ -38,7 +41,7 @@ def main():
         blocks = [text_like(n, i) for i, n in enumerate(sizes)]
         data = np.concatenate(blocks)
         off = np.zeros(len(sizes) + 1, dtype=np.uint64); np.cumsum(sizes, out=off[1:])
-        for params in ((8, 14, 16), (8, 30, 32)):
+        for params in (SWEEP if name.startswith("config5") else ((8, 14, 16), (8, 22, 24), (8, 30, 32))):
             model = rb.AdaptiveTreeModel(rb.Parameters(*params))
             row = {}
             ref = None
