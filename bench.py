@@ -311,15 +311,15 @@ def run_ours(a):
     kdur = {k: (v[0] / v[1] * 1e-3 if v[1] else None) for k, v in ktimes.items()}
     dom = "decode" if (kdur.get("decode") or 0) >= (kdur.get("encode") or 0) else "encode"
     achieved = alg_bytes / kdur[dom] / 1e9
-    cap, cap_src = ncu_capture(workload_name(a), dom + "_lane_kernel")
+    ncu, ncu_src = ncu_capture(workload_name(a), dom + "_lane_kernel")
     roofline = {"bound": "hbm", "kernel": dom + "_lane_kernel", "achieved": round(achieved, 2), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": cap["traffic"] if cap else None,
+                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": ncu["traffic"] if ncu else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": {k: (round(v * 1e3, 3) if v else None) for k, v in kdur.items()},
                 "issue": ({"bound": "per-SM warp-instruction issue (4/clk/SM), the binding resource of this path",
-                           "issue_active_pct_of_peak": cap["issue_active_pct"],
-                           "warp_inst_per_symbol_step": cap["warp_inst_per_symbol_step"],
-                           "source": cap_src} if cap else None),
+                           "issue_active_pct_of_peak": ncu["issue_active_pct"],
+                           "warp_inst_per_symbol_step": ncu["warp_inst_per_symbol_step"],
+                           "source": ncu_src} if ncu else None),
                 "note": "HBM is not the binding resource: a stream is a serial dependency chain, so the kernels "
                         "are bound by instruction issue / latency; frac is reported against HBM as the contract asks"}
 
