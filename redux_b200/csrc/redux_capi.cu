@@ -155,15 +155,9 @@ int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, P
         return fail(ctx, REDUX_UNSUPPORTED, "device path implements symbol_bits == 8 only");
     if (max_block_len > 0xFFFFFFF0ull)
         return fail(ctx, REDUX_UNSUPPORTED, "blocks longer than 2^32-16 bytes are not supported");
-    pl->f = p->freq_bits; pl->c = p->code_bits;
-    pl->cls = arith_class(pl->f, pl->c);
-    const uint64_t fmax = ((uint64_t)1 << pl->f) - 1;
-    pl->tcap = (uint32_t)(fmax - kNsym);                       // f <= 31 -> fits
-    const uint64_t updates = std::min<uint64_t>(max_block_len, pl->tcap);
-    pl->wide_table = updates > 65536;                          // u16 increments suffice otherwise
-    pl->magic_len = (uint32_t)updates + 2;                   // positions 0..updates, +1 read-ahead
-    const uint64_t bound = redux_compress_bound(max_block_len, pl->c);
-    pl->slot_stride = ((bound + 15) & ~(uint64_t)15) + 16;
+    const LanePlan lp = lane_plan(p->freq_bits, p->code_bits, max_block_len);
+    pl->f = lp.f; pl->c = lp.c; pl->cls = lp.cls; pl->tcap = lp.tcap; pl->wide_table = lp.wide_table;
+    pl->magic_len = lp.magic_len; pl->slot_stride = lp.slot_stride;
     return REDUX_OK;
 }
 

@@ -152,6 +152,27 @@ RDX_HD Renorm<T> renorm(T low, T high, uint32_t c) {
     return r;
 }
 
+// Shape of one lane-kernel launch derived from (freq_bits, code_bits) and the longest block: arithmetic
+// class, number of model updates before the freeze (FMAX - NSYM, adaptive_tree.rs:84), table entry width,
+// reciprocal-table length and the per-block worst-case output slot ((len+1) symbols x code_bits bits,
+// SURVEY.md A.4).  Shared by the host front end (redux_capi.cu) and the test harness.
+struct LanePlan {
+    int cls; uint32_t f, c, tcap; bool wide_table; uint32_t magic_len; uint64_t slot_stride;
+};
+RDX_HD LanePlan lane_plan(uint32_t f, uint32_t c, uint64_t max_block_len) {
+    LanePlan pl;
+    pl.f = f; pl.c = c;
+    pl.cls = arith_class(f, c);
+    const uint64_t fmax = ((uint64_t)1 << f) - 1;
+    pl.tcap = (uint32_t)(fmax - kNsym);                        // f <= 31 -> fits
+    const uint64_t updates = max_block_len < pl.tcap ? max_block_len : pl.tcap;
+    pl.wide_table = updates > 65536;                           // u16 increments suffice otherwise
+    pl.magic_len = (uint32_t)updates + 2;                      // positions 0..updates, +1 read-ahead
+    const uint64_t bound = ((max_block_len + 1) * (uint64_t)c + 7) / 8;
+    pl.slot_stride = ((bound + 15) & ~(uint64_t)15) + 16;
+    return pl;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Synthetic mixed-entropy blocks (BASELINE.json configs 3-4).  Counter-based splitmix64 so that the
 // GPU can fill any 8-byte group independently: draw(block, w) = mix(seed + block*K + (w+1)*GAMMA).

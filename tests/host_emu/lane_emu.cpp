@@ -1,0 +1,98 @@
+// lane_emu.cpp -- TEST INFRASTRUCTURE: runs the lane kernels of redux_b200/csrc/redux_lane_codec.cuh on
+// the CPU, thread by thread, through tests/host_emu/cuda_shim.h (see there for why that is exact).
+// Built by tests/test_host_emu.py with g++; compared there against the oracle.  Not part of the product.
+#include "cuda_shim.h"
+
+#include <vector>
+
+thread_local EmuIdx threadIdx, blockIdx, blockDim, gridDim;
+
+#include "../../redux_b200/csrc/redux_lane_codec.cuh"
+
+namespace rdx {
+// dynamic shared memory of one CTA: 7 warps x 256 nodes x 32 lanes x 4 B
+uint4 smem_u4[kLaneWarpsPerCta * kTabNodes * 32 * 4 / 16];
+}
+
+using namespace rdx;
+
+namespace {
+
+std::vector<uint8_t> build_magic(const LanePlan &pl)
+{
+    std::vector<uint8_t> buf;
+    if (pl.cls == kHuge) return buf;
+    const uint32_t nbits = pl.f + pl.c;
+    if (pl.cls == kNarrow) {
+        buf.resize(sizeof(Magic32) * pl.magic_len);
+        Magic32 *m = reinterpret_cast<Magic32 *>(buf.data());
+        for (uint32_t i = 0; i < pl.magic_len; ++i) m[i] = make_magic32(kNsym + i, nbits);
+    } else {
+        buf.resize(sizeof(Magic64) * pl.magic_len);
+        Magic64 *m = reinterpret_cast<Magic64 *>(buf.data());
+        for (uint32_t i = 0; i < pl.magic_len; ++i) m[i] = make_magic64(kNsym + i, nbits);
+    }
+    return buf;
+}
+
+template <typename K, typename J>
+void run_grid(K kernel, const J &job, uint64_t n_blocks)
+{
+    const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
+    blockDim.x = kLaneThreads; blockDim.y = blockDim.z = 1;
+    gridDim.x = grid; gridDim.y = gridDim.z = 1;
+    for (uint32_t b = 0; b < grid; ++b)
+        for (uint32_t t = 0; t < (uint32_t)kLaneThreads; ++t) {
+            blockIdx.x = b; threadIdx.x = t;
+            kernel(job);
+        }
+}
+
+}  // namespace
+
+extern "C" uint64_t emu_slot_stride(uint32_t f, uint32_t c, uint64_t max_block_len)
+{
+    return lane_plan(f, c, max_block_len).slot_stride;
+}
+
+// force_wide_table: -1 = as the front end would choose, 0 = u16 entries, 1 = u32 entries
+extern "C" int emu_encode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, int force_wide_table,
+                               const uint8_t *in, const uint64_t *in_off, uint64_t n_blocks,
+                               uint8_t *slots, uint32_t *sizes, int32_t *status)
+{
+    LanePlan pl = lane_plan(f, c, max_block_len);
+    if (force_wide_table >= 0) pl.wide_table = force_wide_table != 0;
+    std::vector<uint8_t> magic = build_magic(pl);
+    LaneEncJob job;
+    job.in = in; job.in_off = in_off; job.n_blocks = n_blocks;
+    job.slots = slots; job.slot_stride = pl.slot_stride; job.sizes = sizes; job.status = status;
+    job.magic = magic.data(); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+#define RUN(TW) \
+    (pl.cls == kNarrow ? run_grid(encode_lane_kernel<TW, kNarrow>, job, n_blocks) : \
+     pl.cls == kWide   ? run_grid(encode_lane_kernel<TW, kWide>, job, n_blocks)   : \
+                         run_grid(encode_lane_kernel<TW, kHuge>, job, n_blocks))
+    if (pl.wide_table) RUN(uint32_t); else RUN(uint16_t);
+#undef RUN
+    return 0;
+}
+
+extern "C" int emu_decode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, int force_wide_table,
+                               const uint8_t *comp, const uint64_t *comp_off, uint64_t n_blocks,
+                               uint8_t *raw, const uint64_t *raw_off, uint64_t *raw_len,
+                               uint64_t *consumed, int32_t *status)
+{
+    LanePlan pl = lane_plan(f, c, max_block_len);
+    if (force_wide_table >= 0) pl.wide_table = force_wide_table != 0;
+    std::vector<uint8_t> magic = build_magic(pl);
+    LaneDecJob job;
+    job.comp = comp; job.comp_off = comp_off; job.n_blocks = n_blocks;
+    job.raw = raw; job.raw_off = raw_off; job.raw_len = raw_len; job.consumed = consumed;
+    job.status = status; job.magic = magic.data(); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+#define RUN(TW) \
+    (pl.cls == kNarrow ? run_grid(decode_lane_kernel<TW, kNarrow>, job, n_blocks) : \
+     pl.cls == kWide   ? run_grid(decode_lane_kernel<TW, kWide>, job, n_blocks)   : \
+                         run_grid(decode_lane_kernel<TW, kHuge>, job, n_blocks))
+    if (pl.wide_table) RUN(uint32_t); else RUN(uint16_t);
+#undef RUN
+    return 0;
+}
