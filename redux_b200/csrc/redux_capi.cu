@@ -7,7 +7,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -17,6 +19,7 @@
 #include "redux_batch_kernels.cuh"
 #include "redux_common.cuh"
 #include "redux_lane_codec.cuh"
+#include "redux_lane_al.cuh"
 #include "redux_warp_codec.cuh"
 
 using namespace rdx;
@@ -123,6 +126,11 @@ cudaError_t configure_kernels()
     RDX_CFG((decode_lane_kernel<uint16_t, kNarrow>), s16) RDX_CFG((decode_lane_kernel<uint32_t, kNarrow>), s32)
     RDX_CFG((decode_lane_kernel<uint16_t, kWide>), s16)   RDX_CFG((decode_lane_kernel<uint32_t, kWide>), s32)
     RDX_CFG((decode_lane_kernel<uint16_t, kHuge>), s16)   RDX_CFG((decode_lane_kernel<uint32_t, kHuge>), s32)
+    // tuned kernels for code_bits <= 31 (redux_lane_al.cuh); NARROW tables always hold full tree values
+    RDX_CFG((encode_lane_al_kernel<uint16_t, kNarrow, true>), s16) RDX_CFG((decode_lane_al_kernel<uint16_t, kNarrow, true>), s16)
+    RDX_CFG((encode_lane_al_kernel<uint16_t, kWide, true>), s16)   RDX_CFG((decode_lane_al_kernel<uint16_t, kWide, true>), s16)
+    RDX_CFG((encode_lane_al_kernel<uint16_t, kWide, false>), s16)  RDX_CFG((decode_lane_al_kernel<uint16_t, kWide, false>), s16)
+    RDX_CFG((encode_lane_al_kernel<uint32_t, kWide, true>), s32)   RDX_CFG((decode_lane_al_kernel<uint32_t, kWide, true>), s32)
 #undef RDX_CFG
     return cudaSuccess;
 }
@@ -130,6 +138,7 @@ cudaError_t configure_kernels()
 // Shape of one launch derived from the parameters and the longest block.
 struct Plan {
     int cls; uint32_t f, c, tcap; bool wide_table; uint32_t magic_len; uint64_t slot_stride;
+    bool aligned = false, full_table = false;   // see LanePlan
     bool warp = false;      // one stream per warp (latency mapping) instead of one per lane
 };
 
@@ -158,6 +167,7 @@ int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, P
     const LanePlan lp = lane_plan(p->freq_bits, p->code_bits, max_block_len);
     pl->f = lp.f; pl->c = lp.c; pl->cls = lp.cls; pl->tcap = lp.tcap; pl->wide_table = lp.wide_table;
     pl->magic_len = lp.magic_len; pl->slot_stride = lp.slot_stride;
+    pl->aligned = lp.aligned; pl->full_table = lp.full_table;
     return REDUX_OK;
 }
 
@@ -197,6 +207,22 @@ void launch_decode(int cls, const LaneDecJob &job, uint32_t grid, size_t smem, c
     if (cls == kNarrow)    decode_lane_kernel<TW, kNarrow><<<grid, kLaneThreads, smem, s>>>(job);
     else if (cls == kWide) decode_lane_kernel<TW, kWide><<<grid, kLaneThreads, smem, s>>>(job);
     else                   decode_lane_kernel<TW, kHuge><<<grid, kLaneThreads, smem, s>>>(job);
+}
+
+// code_bits <= 31: the tuned kernels.  NARROW implies freq_bits <= 14, i.e. at most 16,126 updates: u16 FULL.
+void launch_encode_al(const Plan &pl, const LaneEncJob &job, uint32_t grid, size_t smem, cudaStream_t s)
+{
+    if (pl.cls == kNarrow)   encode_lane_al_kernel<uint16_t, kNarrow, true><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (pl.wide_table)  encode_lane_al_kernel<uint32_t, kWide, true><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (pl.full_table)  encode_lane_al_kernel<uint16_t, kWide, true><<<grid, kLaneThreads, smem, s>>>(job);
+    else                     encode_lane_al_kernel<uint16_t, kWide, false><<<grid, kLaneThreads, smem, s>>>(job);
+}
+void launch_decode_al(const Plan &pl, const LaneDecJob &job, uint32_t grid, size_t smem, cudaStream_t s)
+{
+    if (pl.cls == kNarrow)   decode_lane_al_kernel<uint16_t, kNarrow, true><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (pl.wide_table)  decode_lane_al_kernel<uint32_t, kWide, true><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (pl.full_table)  decode_lane_al_kernel<uint16_t, kWide, true><<<grid, kLaneThreads, smem, s>>>(job);
+    else                     decode_lane_al_kernel<uint16_t, kWide, false><<<grid, kLaneThreads, smem, s>>>(job);
 }
 
 void launch_encode_warp(int cls, const LaneEncJob &job, cudaStream_t s)
@@ -455,11 +481,13 @@ int encode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     job.slots = slots; job.slot_stride = pl.slot_stride;
     job.sizes = sizes; job.status = d_status;
     job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    job.one = pl.c <= 31 ? 1u << (32 - pl.c) : 0u;
     const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
     const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
     {
         KernelTimer kt(ctx, device, s, REDUX_KERNEL_ENCODE);
         if (pl.warp)            launch_encode_warp(pl.cls, job, s);
+        else if (pl.aligned)    launch_encode_al(pl, job, grid, smem, s);
         else if (pl.wide_table) launch_encode<uint32_t>(pl.cls, job, grid, smem, s);
         else                    launch_encode<uint16_t>(pl.cls, job, grid, smem, s);
     }
@@ -491,11 +519,13 @@ int decode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     job.comp = d_comp; job.comp_off = d_comp_off; job.n_blocks = n_blocks;
     job.raw = d_raw; job.raw_off = d_raw_off; job.raw_len = d_raw_lens; job.consumed = d_consumed;
     job.status = d_status; job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    job.one = pl.c <= 31 ? 1u << (32 - pl.c) : 0u;
     const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
     const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
     {
         KernelTimer kt(ctx, device, s, REDUX_KERNEL_DECODE);
         if (pl.warp)            launch_decode_warp(pl.cls, job, s);
+        else if (pl.aligned)    launch_decode_al(pl, job, grid, smem, s);
         else if (pl.wide_table) launch_decode<uint32_t>(pl.cls, job, grid, smem, s);
         else                    launch_decode<uint16_t>(pl.cls, job, grid, smem, s);
     }
@@ -593,6 +623,18 @@ namespace {
 
 struct Shard { uint64_t first, count; };
 
+// REDUX_TRACE=1: host-side timeline of the pipelined host-buffer calls on stderr (tuning aid).
+struct Trace {
+    bool on; std::chrono::steady_clock::time_point t0;
+    Trace() : on(std::getenv("REDUX_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what, long k = -1) const {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (k >= 0) fprintf(stderr, "[redux trace] %8.2f ms  %s %ld\n", ms, what, k);
+        else fprintf(stderr, "[redux trace] %8.2f ms  %s\n", ms, what);
+    }
+};
+
 std::vector<Shard> make_shards(uint64_t n_blocks, size_t n_dev)
 {
     // contiguous block-index ranges; same rule as redux_debug_shard
@@ -679,6 +721,7 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
                  int32_t *status, EncShardOut *res)
 {
     (void)kind;
+    Trace tr;
     DeviceGuard g(d->device);
     const uint64_t base = in_off[sh.first], bytes = in_off[sh.first + sh.count] - base;
     uint64_t max_len = 0;
@@ -755,12 +798,14 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
             return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline enqueue", e);
         }
     }
+    tr.mark("encode: all chunks enqueued");
     // in order: offsets of chunk k become shard-local offsets; its bytes go out while later chunks run
     uint64_t pos = 0;
     for (size_t k = 0; k < nc; ++k) {
         const Shard c = res->chunks[k];
         cudaError_t e = cudaEventSynchronize(evs.ev[k]);
         if (e != cudaSuccess) { drain(d); (void)cudaGetLastError(); return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline", e); }
+        tr.mark("encode: chunk done", (long)k);
         const uint64_t *lo = h_ooff + c.first + k;
         for (uint64_t i = 0; i <= c.count; ++i) res->local_off[c.first + i] = pos + lo[i];
         std::memcpy(status + c.first, h_status + c.first, c.count * sizeof(int32_t));
@@ -777,6 +822,7 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     }
     res->total = pos;
     CU_TRY(ctx, cudaStreamSynchronize(d->copy));
+    tr.mark("encode: last D2H done");
     return REDUX_OK;
 }
 
@@ -849,6 +895,7 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
                  uint64_t *raw_lens, uint64_t *consumed, int32_t *status)
 {
     (void)kind;
+    Trace tr;
     DeviceGuard g(d->device);
     const uint64_t cbase = comp_off[sh.first], cbytes = comp_off[sh.first + sh.count] - cbase;
     const uint64_t rbase = raw_off[sh.first], rbytes = raw_off[sh.first + sh.count] - rbase;
@@ -918,7 +965,8 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
             return fail(ctx, REDUX_CUDA_ERROR, "decode pipeline enqueue", e);
         }
     }
-    for (int i = 0; i < kPipeStreams; ++i) CU_TRY(ctx, cudaStreamSynchronize(d->pipe[i]));
+    tr.mark("decode: all chunks enqueued");
+    for (int i = 0; i < kPipeStreams; ++i) { CU_TRY(ctx, cudaStreamSynchronize(d->pipe[i])); tr.mark("decode: stream drained", i); }
     std::memcpy(raw_lens + sh.first, h_len, sh.count * sizeof(uint64_t));
     std::memcpy(consumed + sh.first, h_cons, sh.count * sizeof(uint64_t));
     std::memcpy(status + sh.first, h_status, sh.count * sizeof(int32_t));

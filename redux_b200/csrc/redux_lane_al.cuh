@@ -1,0 +1,490 @@
+// redux_lane_al.cuh -- the tuned lane kernels for code_bits <= 31 (32-bit coder state): one stream per
+// lane exactly as in redux_lane_codec.cuh (same table layout, same jobs, same bytes), with the
+// instruction count per symbol cut where profiles/r01_final_* showed the issue slots going:
+//   * LEFT-ALIGNED coder state.  low/high (src/codec.rs:11-24) live in the top c bits of a 32-bit
+//     register (high's spare low bits are ones, low's zeros).  The closed-form renormalisation of
+//     src/codec.rs:62-89 then needs no code_bits arithmetic at all: n1 = clz(low ^ high) and
+//     k = clz(~((low & ~high) << (n1+1))) are one FLO.SH each (bfind.shiftamt; neither operand can be
+//     zero because of the spare bits), the settled bits are the top n1 bits of low (one funnel shift) and
+//     high refills with ones through a funnel shift;
+//   * the decoder's code value (src/codec.rs:124-158) is a 32-bit WINDOW into the compressed stream whose
+//     top c bits are the value and whose low bits are look-ahead; E1/E2 shifts are a funnel shift that
+//     pulls the following stream bits in, E3 shifts keep the MSB and drop the bits below it -- 4
+//     instructions instead of extracting n bits and merging them;
+//   * branch-free pending-bit emission (put_bit, src/codec.rs:39-46) and a word-indexed packer;
+//   * the adaptive phase shares the Fenwick node addresses between the range query and the update
+//     (adaptive_tree.rs:63-92): node (s | (2^k-1)) + 1 of the update path is the query's node
+//     s & (0xFF << k) plus the constant 2^k, so the update is load/add/store per level with no address
+//     arithmetic, and absent query nodes are masked by value instead of by address;
+//   * FULL tables (whenever the entry type can hold them): nodes store the reference's actual tree
+//     values (adaptive_tree.rs:43-45 initialises tree[i] = lowbit(i)) instead of increments, so neither
+//     the query nor the decoder's descent adds the implicit lowbit terms back.
+// Bit-exactness against the oracle is checked on the CPU by tests/test_host_emu.py (these kernels
+// compiled with g++ through a shim) and on the device by tests/test_gpu_parity.py.
+#pragma once
+#include "redux_common.cuh"
+#include "redux_lane_codec.cuh"
+
+namespace rdx {
+
+// count-leading-zeros of a NON-ZERO word as one instruction (FLO.U32.SH)
+__device__ __forceinline__ uint32_t clz_nz(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+#else
+    return (uint32_t)__builtin_clz(x);
+#endif
+}
+
+// ------------------------------------------------------------------ Fenwick table, v2 access paths
+// Same lane-interleaved storage as LaneTable<TW>.  FULL: node i holds the reference's tree[i]
+// (lowbit(i) + increments); otherwise increments only (u16 entries that must survive 65,536 updates).
+template <typename TW, bool FULL>
+struct LaneTable2 : LaneTable<TW> {
+    using B = LaneTable<TW>;
+    using B::t;
+
+    __device__ __forceinline__ void reset() {
+        uint32_t *w = reinterpret_cast<uint32_t *>(t);
+        constexpr int kWords = kTabNodes * (int)sizeof(TW) / 4;
+        if (!FULL) {
+#pragma unroll 8
+            for (int i = 0; i < kWords; ++i) w[i * 32] = 0;
+        } else if (sizeof(TW) == 2) {
+            // word m = nodes (2m, 2m+1): lowbit(2m) = 2*lowbit(m) (node 0 stays 0), lowbit(2m+1) = 1
+#pragma unroll 8
+            for (int m = 0; m < kWords; ++m) w[m * 32] = (uint32_t)(2 * (m & -m)) | (1u << 16);
+        } else {
+#pragma unroll 8
+            for (int i = 0; i < kWords; ++i) w[i * 32] = (uint32_t)(i & -i);
+        }
+    }
+
+    // (cum(s), cum(s+1)) of adaptive_tree.rs:63-80 and, when UPDATE, update(s+1) of :83-92, sharing the
+    // node addresses.  `updates` = number of updates so far (the unstored node 256 is 256 + updates).
+    template <bool UPDATE>
+    __device__ __forceinline__ void query(uint32_t s, uint32_t updates, uint32_t &cl, uint32_t &ch) {
+        const uint32_t S = s << 5;
+        const uint32_t bothmask = s & (s + 1);                 // set bits above the lowest zero bit
+        const uint32_t q = ~s & 255u;                          // clear bits of s
+        const uint32_t levels = q ? (q ^ (1u << (31 - clz32(q)))) : 0u;   // minus the one that leads to node 256
+        TW *a[8];
+        uint32_t v[8];
+#pragma unroll
+        for (int b = 1; b < 8; ++b) {
+            a[b] = t + (S & (0x1FE0u << b));                   // even node s & (0xFF << b)
+            v[b] = *a[b];
+        }
+        TW *po = t + B::node_index(s | 1u);                    // the odd node of s's pair
+        TW *pn = t + B::node_index(((s | 1u) + 1u) & 255u);    // the even node after it (node 0 when it is 256)
+        const uint32_t xo = *po, xn = *pn;
+        const bool odd = s & 1u, last = s == 255u;
+        uint32_t total, both;
+        if (sizeof(TW) == 2) {
+            // both sums in one register: `total` in the low half, `both` in the high half.  Level b adds
+            // v[b] * W with W = (bit b of s) + (bit b of bothmask) << 16 -- one multiply-add per level instead
+            // of two masked adds.  Neither half can carry: a path sum is at most cum(s) <= 65,535 here.
+            const uint32_t z = s | (bothmask << 16);
+            uint32_t acc = 0;
+#pragma unroll
+            for (int b = 1; b < 8; ++b) acc += v[b] * ((z >> b) & 0x00010001u);
+            total = (acc & 0xFFFFu) + (odd ? xo : 0u);
+            both = acc >> 16;
+        } else {
+            total = odd ? xo : 0u; both = 0;
+#pragma unroll
+            for (int b = 1; b < 8; ++b) {
+                total += (s & (1u << b)) ? v[b] : 0u;
+                both += (bothmask & (1u << b)) ? v[b] : 0u;
+            }
+        }
+        const uint32_t top = odd ? (last ? updates + (FULL ? 256u : 0u) : xn) : xo;
+        cl = total + (FULL ? 0u : s);
+        ch = top + both + (FULL ? 0u : s + 1u);
+        if (UPDATE) {
+            // all loads before all stores: the nodes of one update path are distinct, which the compiler
+            // cannot know, and a load/store/load/store chain would serialise the shared-memory round trips
+            uint32_t u[8];
+#pragma unroll
+            for (int k = 1; k < 8; ++k)                        // (s | (2^k - 1)) + 1 = (s & (0xFF << k)) + 2^k
+                if (levels & (1u << (k - 1))) u[k] = a[k][32 << k];
+            // node s+1 (the odd node for even s, the following even node for odd s; node 256 unstored)
+            if (!last) { TW *p = odd ? pn : po; *p = (TW)((odd ? xn : xo) + 1u); }
+#pragma unroll
+            for (int k = 1; k < 8; ++k)
+                if (levels & (1u << (k - 1))) a[k][32 << k] = (TW)(u[k] + 1u);
+        }
+    }
+
+    // update(s+1) alone (decoder: the search already produced the range)
+    __device__ __forceinline__ void update(uint32_t s) {
+        const uint32_t S = s << 5;
+        const uint32_t q = ~s & 255u;
+        const uint32_t levels = q ? (q ^ (1u << (31 - clz32(q)))) : 0u;
+        TW *p0 = t + B::node_index((s + 1u) & 255u);
+        TW *a[8];
+        uint32_t u[8];
+        const uint32_t u0 = *p0;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            a[k] = t + (S & (0x1FE0u << k)) + (32 << k);
+            if (levels & (1u << (k - 1))) u[k] = *a[k];
+        }
+        if (q) *p0 = (TW)(u0 + 1u);
+#pragma unroll
+        for (int k = 1; k < 8; ++k)
+            if (levels & (1u << (k - 1))) *a[k] = (TW)(u[k] + 1u);
+    }
+
+    // Frozen model (adaptive_tree.rs:84): rewrite the tree in place as the cumulative array of
+    // AdaptiveLinearModel (adaptive_linear.rs:26-28): C[i] = cum(i) (FULL) or cum(i) - i.  Descending i
+    // only reads nodes <= i, which are still tree nodes.
+    __device__ __forceinline__ void freeze_to_cumulative() {
+        for (uint32_t i = 255; i >= 1; --i) {
+            uint32_t sum = 0;
+            for (uint32_t x = i; x; x &= x - 1) sum += t[B::node_index(x)];
+            t[B::node_index(i)] = (TW)sum;
+        }
+    }
+    __device__ __forceinline__ void query_frozen(uint32_t s, uint32_t count, uint32_t &cl, uint32_t &ch) const {
+        uint32_t lo, hi;
+        if (sizeof(TW) == 2) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(t);
+            const uint32_t w0 = w[(s >> 1) << 5], w1 = w[(((s + 1) >> 1) & 127u) << 5];
+            const bool odd = s & 1u;
+            lo = odd ? (w0 >> 16) : (w0 & 0xFFFFu);
+            hi = odd ? (w1 & 0xFFFFu) : (w0 >> 16);
+        } else {
+            lo = t[s << 5];
+            hi = t[((s + 1) & 255u) << 5];
+        }
+        cl = lo + (FULL ? 0u : s);
+        ch = (s == 255u) ? count - 1 : hi + (FULL ? 0u : s + 1u);
+    }
+};
+
+// ------------------------------------------------------------------ bit packer, word-indexed
+struct BitSink2 {
+    uint64_t acc;      // newest bit at bit 0
+    uint32_t nb;       // valid bits in acc, < 32 between calls
+    uint32_t wi;       // next output word
+    uint32_t *w0;      // slot (16-byte aligned)
+
+    __device__ __forceinline__ void init(uint8_t *slot) { acc = 0; nb = 0; wi = 0; w0 = (uint32_t *)slot; }
+    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {          // n <= 32, v < 2^n
+        acc = (acc << n) | v;
+        nb += n;
+        if (nb >= 32) {
+            nb -= 32;
+            w0[wi++] = __byte_perm((uint32_t)(acc >> nb), 0, 0x0123);      // first bit -> MSB of first byte
+        }
+    }
+    // put_bit semantics (src/codec.rs:39-46) for one symbol: `bits` = the n1 settled bits (MSB first),
+    // the first followed by `pend` copies of its inverse; k = this symbol's E3 shifts.  Returns the new
+    // pending count.  [b][pend x !b][rest] as one number is bits + 2^(n1+pend-1) - 2^(n1-1) for either b;
+    // with n1 == 0 nothing is emitted and the pending run grows.
+    __device__ __forceinline__ uint32_t put_code(uint32_t bits, uint32_t n1, uint32_t pend, uint32_t k) {
+        const bool emit = n1 != 0;
+        const uint32_t n = emit ? n1 + pend : 0u;
+        if (n > 32) {                                                       // rare: long E3 run
+            const uint32_t b = (bits >> (n1 - 1)) & 1u;
+            put(b, 1);
+            while (pend > 0) {
+                const uint32_t m = pend < 32 ? pend : 32;
+                put(b ? 0u : (0xFFFFFFFFu >> (32 - m)), m);
+                pend -= m;
+            }
+            if (n1 > 1) put(bits & (0xFFFFFFFFu >> (33 - n1)), n1 - 1);
+        } else {
+            // 2^(x-1) with x = 0 -> 0: clamped funnel shift of (1:0)
+            put(bits + __funnelshift_lc(0u, 1u, n - 1u) - __funnelshift_lc(0u, 1u, n1 - 1u), n);
+        }
+        return (emit ? 0u : pend) + k;
+    }
+    __device__ __forceinline__ uint32_t finish() {                          // flush_bits (src/bitio/mod.rs:183-198)
+        const uint32_t bytes = wi * 4 + (nb + 7) / 8;
+        if (nb) w0[wi] = __byte_perm((uint32_t)(acc << (32 - nb)), 0, 0x0123);
+        return bytes;
+    }
+};
+
+// One coding step on left-aligned state (src/codec.rs:55-89).  L: low << sh, H: (high << sh) | ones.
+// Returns the number of shifts.
+template <int CLS>
+__device__ __forceinline__ uint32_t encode_step_al(uint32_t &L, uint32_t &H, uint32_t &pend, BitSink2 &sink,
+                                                   uint32_t cl, uint32_t ch, uint32_t count,
+                                                   const typename Cls<CLS>::M &g, uint32_t sh, uint32_t one)
+{
+    using C = Cls<CLS>;
+    using P = typename C::P;
+    const uint32_t rm1 = (H - L) >> sh;                            // range - 1  (:58)
+    const P nh = C::mulr(ch, rm1), nl = C::mulr(cl, rm1);
+    // `one` == 1 << sh, handed in as an opaque value so that quotient * one + L stays a single IMAD
+    const uint32_t nh2 = ~((uint32_t)C::divc(nh, g, count) * one + (L - 1u));   // ~high' (:59)
+    const uint32_t l2 = (uint32_t)C::divc(nl, g, count) * one + L;              // low'   (:60)
+    const uint32_t n1 = clz_nz(~(l2 ^ nh2));                       // E1/E2 shifts (:63-74)
+    const uint32_t k = clz_nz(~(((l2 & nh2) << 1) << n1));         // E3 shifts (:75-83)
+    const uint32_t n = n1 + k;                                     // <= c <= 31
+    pend = sink.put_code(__funnelshift_l(l2, 0u, n1), n1, pend, k);
+    L = (l2 << n) & 0x7FFFFFFFu;                                   // :87-88 after the E3 subtraction
+    H = ~(nh2 << n) | 0x80000000u;                                 // high refills with ones
+    return n;
+}
+
+// ------------------------------------------------------------------ encoder
+template <typename TW, int CLS, bool FULL>
+__global__ void __launch_bounds__(kLaneThreads, 2)
+encode_lane_al_kernel(const LaneEncJob job)
+{
+    using C = Cls<CLS>;
+    using M = typename C::M;
+    extern __shared__ uint4 smem_u4[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t blk = (uint64_t)blockIdx.x * kLaneThreads + threadIdx.x;
+    if (blk >= job.n_blocks) return;
+
+    LaneTable2<TW, FULL> tab;
+    tab.init(smem_u4, warp, lane);
+    tab.reset();
+
+    const uint64_t off = job.in_off[blk];
+    const uint32_t len = (uint32_t)(job.in_off[blk + 1] - off);
+    const uint32_t c = job.c, sh = 32 - c, one = job.one;
+    const M *magic = reinterpret_cast<const M *>(job.magic);
+    const uint32_t tcap = job.tcap;
+
+    ByteSource src;
+    src.init(job.in + off, len);
+    BitSink2 sink;
+    sink.init(job.slots + blk * job.slot_stride);
+    uint32_t L = 0, H = 0xFFFFFFFFu;                       // low = 0, high = code_max (src/codec.rs:30-31)
+    uint32_t pend = 0;
+
+    // adaptive phase: the model still learns, count grows by one per symbol
+    const uint32_t n_adapt = len < tcap ? len : tcap;
+    uint32_t t = 0;
+    M gn = C::ldm(magic);                                  // reciprocal of position t, loaded one ahead
+    for (; t < n_adapt; ++t) {
+        const M g = gn;
+        gn = C::ldm(magic + t + 1);
+        const uint32_t sym = src.next();
+        uint32_t cl, ch;
+        tab.template query<true>(sym, t, cl, ch);
+        encode_step_al<CLS>(L, H, pend, sink, cl, ch, kNsym + t, g, sh, one);
+    }
+    // frozen phase (adaptive_tree.rs:84): total == FMAX, table and reciprocal are constant
+    const M gf = gn;                                       // = magic[n_adapt]
+    const uint32_t countf = kNsym + n_adapt;
+    if (t < len) {
+        tab.freeze_to_cumulative();
+        // the lookup does not depend on the coder state: look symbol t+1 up before coding
+        // symbol t, so the shared-memory latency overlaps the range update
+        uint32_t cl, ch;
+        tab.query_frozen(src.next(), countf, cl, ch);
+        for (; t + 1 < len; ++t) {
+            const uint32_t cl_cur = cl, ch_cur = ch;
+            tab.query_frozen(src.next(), countf, cl, ch);
+            encode_step_al<CLS>(L, H, pend, sink, cl_cur, ch_cur, countf, gf, sh, one);
+        }
+        encode_step_al<CLS>(L, H, pend, sink, cl, ch, countf, gf, sh, one);
+        ++t;
+    }
+    // EOF symbol: cum(256) = total - 1, then the tail of src/codec.rs:91-99: the remaining `extra` MSBs of
+    // low, the first of them carrying the pending run, then flush
+    const uint32_t shifts = encode_step_al<CLS>(L, H, pend, sink, countf - 1, countf, countf, gf, sh, one);
+    const uint32_t extra = c - shifts;
+    sink.put_code(__funnelshift_l(L, 0u, extra), extra, pend, 0);
+    job.sizes[blk] = sink.finish();
+    job.status[blk] = 0;
+}
+
+// ------------------------------------------------------------------ bit window (decoder input)
+// w0:w1 are two consecutive big-endian stream words; win() = the 32 stream bits starting at bit `pos`
+// of w0.  The word after w1 is always already in flight (`nxt`, still in memory byte order).
+struct BitWindow {
+    uint32_t w0, w1, nxt, pos;
+    const uint32_t *base;
+    uint32_t idx, last;     // next word to prefetch / last word that may be read
+
+    static __device__ __forceinline__ uint32_t swap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+    __device__ __forceinline__ uint32_t ld() {
+        const uint32_t v = __ldg(base + (idx < last ? idx : last));        // past the end: re-read, never used
+        ++idx;
+        return v;
+    }
+    // len >= 1.  Returns the first 32 bits of the stream and leaves the window right after them.
+    __device__ __forceinline__ uint32_t init(const uint8_t *src, uint32_t len) {
+        const uintptr_t a = (uintptr_t)src;
+        const uint32_t mis = (uint32_t)(a & 3);
+        base = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        last = ((mis + len + 3) >> 2) - 1;
+        idx = 0;
+        pos = 8 * mis;
+        w0 = swap(ld()); w1 = swap(ld()); nxt = ld();
+        const uint32_t first = win();
+        w0 = w1; w1 = swap(nxt); nxt = ld();
+        return first;
+    }
+    __device__ __forceinline__ uint32_t win() const { return __funnelshift_l(w1, w0, pos); }
+    __device__ __forceinline__ void advance(uint32_t n) {                   // n <= 31
+        pos += n;
+        if (pos >= 32) { pos -= 32; w0 = w1; w1 = swap(nxt); nxt = ld(); }
+    }
+};
+
+// ------------------------------------------------------------------ decoder
+template <typename TW, int CLS, bool FULL>
+struct LaneDecoderAl {
+    using C = Cls<CLS>;
+    using P = typename C::P;
+    using M = typename C::M;
+    LaneTable2<TW, FULL> tab;
+    BitWindow bw;
+    ByteSink out;
+    uint32_t L, H, V;    // left-aligned low / high (src/codec.rs:11-24) and the code-value window
+    uint32_t sh, one, t, left;   // one == 1 << sh, opaque to the compiler (keeps q * one + L an IMAD)
+    int32_t st;          // 0 running, -1 EOF symbol decoded (success), >0 error code
+
+    // Decodes symbols while t < t_end.  ADAPT: the model still learns (count = 257 + t, one reciprocal per
+    // position); otherwise the table is frozen at `count_frozen`.  PEEK: the output slot is full -- decode
+    // one more symbol only to tell a complete stream (EOF next) from Err(Eof) and from OUT_CAPACITY.
+    template <bool ADAPT, bool PEEK>
+    __device__ __forceinline__ void run(uint32_t t_end, const M *magic, uint32_t count_frozen, const M &g_frozen) {
+        M gn = ADAPT ? C::ldm(magic + t) : g_frozen;          // reciprocal of position t, loaded one ahead
+        while (t < t_end) {
+            const uint32_t count = ADAPT ? kNsym + t : count_frozen;
+            const M g = gn;
+            if (ADAPT && !PEEK) gn = C::ldm(magic + t + 1);
+            // src/codec.rs:129-131 without the division: find i with cum(i)*range <= X < cum(i+1)*range,
+            // X = (value-low+1)*count - 1
+            const uint32_t rm1 = (H - L) >> sh;
+            const P X = C::mulr(count, (V - L) >> sh) - 1;
+            P plo = 0, phi = C::mulr(count - 1, rm1);             // node 256 = cum(256) = count - 1
+            uint32_t I = 0;                                       // i * 32
+            const bool is_eof = X >= phi;
+            if (CLS == kNarrow) {
+                // two tree levels per round (adaptive_tree.rs:119-127 unrolled by two): the candidates i+m,
+                // i+m/2 and i+m+m/2 are loaded together -- 4 dependent shared-memory round trips, not 8
+#pragma unroll
+                for (int m = 128; m >= 2; m >>= 2) {
+                    const int h = m >> 1;
+                    const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;      // nodes i+1, i+3 are odd
+                    const uint32_t a = (FULL ? 0u : (uint32_t)m) + tab.t[I + (uint32_t)(m << 5)];
+                    const uint32_t b = (FULL ? 0u : (uint32_t)h) + tab.t[(int)I + (h << 5) + oddadj];
+                    const uint32_t cc = (FULL ? 0u : (uint32_t)h) + tab.t[(int)I + ((m + h) << 5) + oddadj];
+                    const P pa = C::mul_add(a, rm1, plo);
+                    const P pb = C::mul_add(b, rm1, plo);
+                    const P pc = C::mul_add(cc, rm1, pa);
+                    const bool ra = X >= pa, rb = X >= pb, rc = X >= pc;
+                    const bool r2 = ra ? rc : rb;                                   // second-level decision
+                    const P p2 = ra ? pc : pb;                                      // second-level boundary
+                    const P base = ra ? pa : plo;
+                    phi = r2 ? (ra ? phi : pa) : p2;
+                    plo = r2 ? p2 : base;
+                    I += (ra ? (uint32_t)(m << 5) : 0u) + (r2 ? (uint32_t)(h << 5) : 0u);
+                }
+            } else {
+#pragma unroll
+                for (int m = 128; m >= 2; m >>= 1) {              // even nodes i + m
+                    const uint32_t tv = (FULL ? 0u : (uint32_t)m) + tab.t[I + (uint32_t)(m << 5)];
+                    const P p = C::mul_add(tv, rm1, plo);
+                    const bool right = X >= p;
+                    if (right) { I += (uint32_t)(m << 5); plo = p; } else { phi = p; }
+                }
+                {                                                 // m = 1: odd node i + 1
+                    const uint32_t tv = (FULL ? 0u : 1u) + tab.t[(int)I + 32 + LaneTable<TW>::kOddAdj];
+                    const P p = C::mul_add(tv, rm1, plo);
+                    const bool right = X >= p;
+                    if (right) { I += 32u; plo = p; } else { phi = p; }
+                }
+            }
+            if (is_eof) {                                         // src/codec.rs:136-138: no renorm, no reads
+                st = -1;
+                return;
+            }
+            const uint32_t sym = I >> 5;
+            // src/codec.rs:133-134
+            const uint32_t nh2 = ~((uint32_t)C::divc(phi, g, count) * one + (L - 1u));
+            const uint32_t l2 = (uint32_t)C::divc(plo, g, count) * one + L;
+            if (ADAPT && !PEEK) tab.update(sym);
+            // src/codec.rs:140-158 in closed form
+            const uint32_t n1 = clz_nz(~(l2 ^ nh2));
+            const uint32_t k = clz_nz(~(((l2 & nh2) << 1) << n1));
+            const uint32_t n = n1 + k;
+            if (n > left) { st = 1; left = 0; return; }           // Err(Eof) inside get_bit (:49-52)
+            if (PEEK) { st = 6; return; }                         // a data symbol with nowhere to go
+            left -= n;
+            // E1/E2: shift the window, pulling the next stream bits in; E3: keep the MSB, drop k bits below it
+            const uint32_t win = bw.win();
+            const uint32_t A = __funnelshift_l(win, V, n1);
+            const uint32_t Bv = __funnelshift_l(win << n1, A, k);
+            V = (A & 0x80000000u) | (Bv & 0x7FFFFFFFu);
+            bw.advance(n);
+            L = (l2 << n) & 0x7FFFFFFFu;
+            H = ~(nh2 << n) | 0x80000000u;
+            out.put(sym);
+            ++t;
+        }
+    }
+};
+
+template <typename TW, int CLS, bool FULL>
+__global__ void __launch_bounds__(kLaneThreads, 2)
+decode_lane_al_kernel(const LaneDecJob job)
+{
+    using D = LaneDecoderAl<TW, CLS, FULL>;
+    using M = typename D::M;
+    extern __shared__ uint4 smem_u4[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t blk = (uint64_t)blockIdx.x * kLaneThreads + threadIdx.x;
+    if (blk >= job.n_blocks) return;
+
+    D d;
+    d.tab.init(smem_u4, warp, lane);
+    d.tab.reset();
+
+    const uint64_t coff = job.comp_off[blk];
+    const uint64_t clen = job.comp_off[blk + 1] - coff;
+    const uint64_t roff = job.raw_off[blk];
+    const uint64_t cap64 = job.raw_off[blk + 1] - roff;
+    if (clen >= (1ull << 29)) {                 // 32-bit bit counters; such a stream is not lane work
+        job.raw_len[blk] = 0; job.consumed[blk] = 0; job.status[blk] = 5;
+        return;
+    }
+    const uint32_t c = job.c;
+    const uint32_t cap = cap64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)cap64;
+    const uint32_t total_bits = (uint32_t)clen * 8;
+    d.sh = 32 - c; d.one = job.one;
+    d.out.init(job.raw + roff);
+    d.st = 0; d.t = 0;
+    d.L = 0; d.H = 0xFFFFFFFFu; d.V = 0; d.left = 0;
+    const M *magic = reinterpret_cast<const M *>(job.magic);
+    const uint32_t tcap = job.tcap;
+
+    // src/codec.rs:124-127: prime code_bits bits (Err(Eof) if the stream is shorter)
+    if (total_bits < c) {
+        d.st = 1;
+    } else {
+        d.V = d.bw.init(job.comp + coff, (uint32_t)clen);
+        d.left = total_bits - c;
+    }
+    const M g0 = D::C::ldm(magic);
+    if (d.st == 0) {
+        const uint32_t e1 = tcap < cap ? tcap : cap;
+        d.template run<true, false>(e1, magic, 0, g0);
+        if (d.st == 0 && d.t == cap && cap < tcap) d.template run<true, true>(d.t + 1, magic, 0, g0);
+    }
+    if (d.st == 0) {
+        const M gf = D::C::ldm(magic + tcap);
+        d.template run<false, false>(cap, magic, kNsym + tcap, gf);
+        if (d.st == 0) d.template run<false, true>(d.t + 1, magic, kNsym + tcap, gf);
+    }
+    d.out.finish();
+    job.raw_len[blk] = d.t;
+    job.consumed[blk] = (total_bits - d.left + 7) >> 3;
+    job.status[blk] = d.st < 0 ? 0 : d.st;
+}
+
+}  // namespace rdx

@@ -45,6 +45,7 @@ struct LaneEncJob {
     const void *magic;          // Magic32/Magic64 [magic_len], entry tt <-> count 257+tt
     uint32_t f, c;
     uint32_t tcap;              // FMAX - NSYM: number of model updates before the freeze
+    uint32_t one;               // 1 << (32 - c) for c <= 31 (redux_lane_al.cuh), else 0
 };
 
 struct LaneDecJob {
@@ -59,6 +60,7 @@ struct LaneDecJob {
     const void *magic;
     uint32_t f, c;
     uint32_t tcap;
+    uint32_t one;               // as in LaneEncJob
 };
 
 // ------------------------------------------------------------------ arithmetic class traits

@@ -8,6 +8,7 @@
 thread_local EmuIdx threadIdx, blockIdx, blockDim, gridDim;
 
 #include "../../redux_b200/csrc/redux_lane_codec.cuh"
+#include "../../redux_b200/csrc/redux_lane_al.cuh"
 
 namespace rdx {
 // dynamic shared memory of one CTA: 7 warps x 256 nodes x 32 lanes x 4 B
@@ -55,24 +56,36 @@ extern "C" uint64_t emu_slot_stride(uint32_t f, uint32_t c, uint64_t max_block_l
     return lane_plan(f, c, max_block_len).slot_stride;
 }
 
-// force_wide_table: -1 = as the front end would choose, 0 = u16 entries, 1 = u32 entries
+// force_wide_table: -1 = as the front end would choose, 0 = u16 entries, 1 = u32 entries; +2 = force the
+// generic kernels (redux_lane_codec.cuh) where the tuned ones (redux_lane_al.cuh) would be chosen
 extern "C" int emu_encode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, int force_wide_table,
                                const uint8_t *in, const uint64_t *in_off, uint64_t n_blocks,
                                uint8_t *slots, uint32_t *sizes, int32_t *status)
 {
     LanePlan pl = lane_plan(f, c, max_block_len);
-    if (force_wide_table >= 0) pl.wide_table = force_wide_table != 0;
+    const bool legacy = force_wide_table >= 2;            // 2/3: the generic kernels of redux_lane_codec.cuh
+    if (force_wide_table >= 2) force_wide_table -= 2;
+    if (force_wide_table >= 0) { pl.wide_table = force_wide_table != 0; if (pl.wide_table) pl.full_table = true; }
     std::vector<uint8_t> magic = build_magic(pl);
     LaneEncJob job;
     job.in = in; job.in_off = in_off; job.n_blocks = n_blocks;
     job.slots = slots; job.slot_stride = pl.slot_stride; job.sizes = sizes; job.status = status;
     job.magic = magic.data(); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    job.one = pl.c <= 31 ? 1u << (32 - pl.c) : 0u;
 #define RUN(TW) \
     (pl.cls == kNarrow ? run_grid(encode_lane_kernel<TW, kNarrow>, job, n_blocks) : \
      pl.cls == kWide   ? run_grid(encode_lane_kernel<TW, kWide>, job, n_blocks)   : \
                          run_grid(encode_lane_kernel<TW, kHuge>, job, n_blocks))
-    if (pl.wide_table) RUN(uint32_t); else RUN(uint16_t);
+#define RUN_AL(TW, FULL) \
+    (pl.cls == kNarrow ? run_grid(encode_lane_al_kernel<TW, kNarrow, FULL>, job, n_blocks) : \
+                         run_grid(encode_lane_al_kernel<TW, kWide, FULL>, job, n_blocks))
+    if (pl.aligned && !legacy) {
+        if (pl.wide_table) RUN_AL(uint32_t, true);
+        else if (pl.full_table) RUN_AL(uint16_t, true);
+        else RUN_AL(uint16_t, false);
+    } else if (pl.wide_table) RUN(uint32_t); else RUN(uint16_t);
 #undef RUN
+#undef RUN_AL
     return 0;
 }
 
@@ -82,17 +95,28 @@ extern "C" int emu_decode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, i
                                uint64_t *consumed, int32_t *status)
 {
     LanePlan pl = lane_plan(f, c, max_block_len);
-    if (force_wide_table >= 0) pl.wide_table = force_wide_table != 0;
+    const bool legacy = force_wide_table >= 2;            // 2/3: the generic kernels of redux_lane_codec.cuh
+    if (force_wide_table >= 2) force_wide_table -= 2;
+    if (force_wide_table >= 0) { pl.wide_table = force_wide_table != 0; if (pl.wide_table) pl.full_table = true; }
     std::vector<uint8_t> magic = build_magic(pl);
     LaneDecJob job;
     job.comp = comp; job.comp_off = comp_off; job.n_blocks = n_blocks;
     job.raw = raw; job.raw_off = raw_off; job.raw_len = raw_len; job.consumed = consumed;
     job.status = status; job.magic = magic.data(); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    job.one = pl.c <= 31 ? 1u << (32 - pl.c) : 0u;
 #define RUN(TW) \
     (pl.cls == kNarrow ? run_grid(decode_lane_kernel<TW, kNarrow>, job, n_blocks) : \
      pl.cls == kWide   ? run_grid(decode_lane_kernel<TW, kWide>, job, n_blocks)   : \
                          run_grid(decode_lane_kernel<TW, kHuge>, job, n_blocks))
-    if (pl.wide_table) RUN(uint32_t); else RUN(uint16_t);
+#define RUN_AL(TW, FULL) \
+    (pl.cls == kNarrow ? run_grid(decode_lane_al_kernel<TW, kNarrow, FULL>, job, n_blocks) : \
+                         run_grid(decode_lane_al_kernel<TW, kWide, FULL>, job, n_blocks))
+    if (pl.aligned && !legacy) {
+        if (pl.wide_table) RUN_AL(uint32_t, true);
+        else if (pl.full_table) RUN_AL(uint16_t, true);
+        else RUN_AL(uint16_t, false);
+    } else if (pl.wide_table) RUN(uint32_t); else RUN(uint16_t);
 #undef RUN
+#undef RUN_AL
     return 0;
 }

@@ -24,7 +24,8 @@ SEED = 0x5EED202610180000
 
 def _build():
     srcs = [os.path.join(EMU_DIR, "lane_emu.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"),
-            os.path.join(CSRC, "redux_lane_codec.cuh"), os.path.join(CSRC, "redux_common.cuh")]
+            os.path.join(CSRC, "redux_lane_codec.cuh"), os.path.join(CSRC, "redux_lane_al.cuh"),
+            os.path.join(CSRC, "redux_common.cuh")]
     if os.path.exists(EMU_SO) and all(os.path.getmtime(s) <= os.path.getmtime(EMU_SO) for s in srcs):
         return
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
