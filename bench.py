@@ -224,6 +224,7 @@ def run_ours(a):
 
     import redux_b200 as rb
     from redux_b200 import sharding
+    rb.lib()            # load the C-ABI library before CUDA is initialised (it asks for 32 hardware queues)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -24,6 +24,17 @@
 
 using namespace rdx;
 
+// The pipelined host-buffer API keeps ~18 streams busy per device.  CUDA multiplexes streams onto
+// CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue serialise in
+// submission order, which measured as three chunks of sixteen stalling ~30 ms behind unrelated copies
+// (profiles/r01_e2e_pipeline.md).  The variable is read when the CUDA context is created, so the
+// library asks for 32 queues when it is loaded -- effective whenever that happens before the process
+// initialises CUDA (import order in Python, link order in C); an explicit user setting wins.
+__attribute__((constructor)) static void redux_b200_on_load()
+{
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+}
+
 namespace {
 
 struct MagicEntry { int cls; uint32_t nbits; uint32_t len; void *ptr; };
@@ -117,20 +128,22 @@ cudaError_t allow_smem(K kernel, size_t bytes)
 
 cudaError_t configure_kernels()
 {
-    const size_t s16 = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * 2, s32 = s16 * 2;
+    const size_t s16 = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * 2 + kTabPadBytes;
+    const size_t s32 = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * 4 + kTabPadBytes;
     cudaError_t e;
 #define RDX_CFG(K, BYTES) if ((e = allow_smem(K, BYTES)) != cudaSuccess) return e;
-    RDX_CFG((encode_lane_kernel<uint16_t, kNarrow>), s16) RDX_CFG((encode_lane_kernel<uint32_t, kNarrow>), s32)
-    RDX_CFG((encode_lane_kernel<uint16_t, kWide>), s16)   RDX_CFG((encode_lane_kernel<uint32_t, kWide>), s32)
+    // generic kernels (redux_lane_codec.cuh): code_bits > 32 only
     RDX_CFG((encode_lane_kernel<uint16_t, kHuge>), s16)   RDX_CFG((encode_lane_kernel<uint32_t, kHuge>), s32)
-    RDX_CFG((decode_lane_kernel<uint16_t, kNarrow>), s16) RDX_CFG((decode_lane_kernel<uint32_t, kNarrow>), s32)
-    RDX_CFG((decode_lane_kernel<uint16_t, kWide>), s16)   RDX_CFG((decode_lane_kernel<uint32_t, kWide>), s32)
     RDX_CFG((decode_lane_kernel<uint16_t, kHuge>), s16)   RDX_CFG((decode_lane_kernel<uint32_t, kHuge>), s32)
-    // tuned kernels for code_bits <= 31 (redux_lane_al.cuh); NARROW tables always hold full tree values
-    RDX_CFG((encode_lane_al_kernel<uint16_t, kNarrow, true>), s16) RDX_CFG((decode_lane_al_kernel<uint16_t, kNarrow, true>), s16)
-    RDX_CFG((encode_lane_al_kernel<uint16_t, kWide, true>), s16)   RDX_CFG((decode_lane_al_kernel<uint16_t, kWide, true>), s16)
-    RDX_CFG((encode_lane_al_kernel<uint16_t, kWide, false>), s16)  RDX_CFG((decode_lane_al_kernel<uint16_t, kWide, false>), s16)
-    RDX_CFG((encode_lane_al_kernel<uint32_t, kWide, true>), s32)   RDX_CFG((decode_lane_al_kernel<uint32_t, kWide, true>), s32)
+    // tuned kernels (redux_lane_al.cuh): <entry type, class, full tree values, code_bits == 32>.
+    // NARROW (c + f <= 30) implies at most 16,126 updates: always u16 entries with full values.
+    RDX_CFG((encode_lane_al_kernel<uint16_t, kNarrow, true, false>), s16) RDX_CFG((decode_lane_al_kernel<uint16_t, kNarrow, true, false>), s16)
+#define RDX_CFG_WIDE(C32) \
+    RDX_CFG((encode_lane_al_kernel<uint16_t, kWide, true, C32>), s16)  RDX_CFG((decode_lane_al_kernel<uint16_t, kWide, true, C32>), s16) \
+    RDX_CFG((encode_lane_al_kernel<uint16_t, kWide, false, C32>), s16) RDX_CFG((decode_lane_al_kernel<uint16_t, kWide, false, C32>), s16) \
+    RDX_CFG((encode_lane_al_kernel<uint32_t, kWide, true, C32>), s32)  RDX_CFG((decode_lane_al_kernel<uint32_t, kWide, true, C32>), s32)
+    RDX_CFG_WIDE(false) RDX_CFG_WIDE(true)
+#undef RDX_CFG_WIDE
 #undef RDX_CFG
     return cudaSuccess;
 }
@@ -194,35 +207,44 @@ int get_magic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const Plan &p
     return REDUX_OK;
 }
 
+// code_bits > 32: the generic kernels
 template <typename TW>
-void launch_encode(int cls, const LaneEncJob &job, uint32_t grid, size_t smem, cudaStream_t s)
+void launch_encode(const LaneEncJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {
-    if (cls == kNarrow)    encode_lane_kernel<TW, kNarrow><<<grid, kLaneThreads, smem, s>>>(job);
-    else if (cls == kWide) encode_lane_kernel<TW, kWide><<<grid, kLaneThreads, smem, s>>>(job);
-    else                   encode_lane_kernel<TW, kHuge><<<grid, kLaneThreads, smem, s>>>(job);
+    encode_lane_kernel<TW, kHuge><<<grid, kLaneThreads, smem, s>>>(job);
 }
 template <typename TW>
-void launch_decode(int cls, const LaneDecJob &job, uint32_t grid, size_t smem, cudaStream_t s)
+void launch_decode(const LaneDecJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {
-    if (cls == kNarrow)    decode_lane_kernel<TW, kNarrow><<<grid, kLaneThreads, smem, s>>>(job);
-    else if (cls == kWide) decode_lane_kernel<TW, kWide><<<grid, kLaneThreads, smem, s>>>(job);
-    else                   decode_lane_kernel<TW, kHuge><<<grid, kLaneThreads, smem, s>>>(job);
+    decode_lane_kernel<TW, kHuge><<<grid, kLaneThreads, smem, s>>>(job);
 }
 
-// code_bits <= 31: the tuned kernels.  NARROW implies freq_bits <= 14, i.e. at most 16,126 updates: u16 FULL.
+// code_bits <= 32: the tuned kernels
+template <bool C32>
+void launch_encode_wide(const Plan &pl, const LaneEncJob &job, uint32_t grid, size_t smem, cudaStream_t s)
+{
+    if (pl.wide_table)       encode_lane_al_kernel<uint32_t, kWide, true, C32><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (pl.full_table)  encode_lane_al_kernel<uint16_t, kWide, true, C32><<<grid, kLaneThreads, smem, s>>>(job);
+    else                     encode_lane_al_kernel<uint16_t, kWide, false, C32><<<grid, kLaneThreads, smem, s>>>(job);
+}
+template <bool C32>
+void launch_decode_wide(const Plan &pl, const LaneDecJob &job, uint32_t grid, size_t smem, cudaStream_t s)
+{
+    if (pl.wide_table)       decode_lane_al_kernel<uint32_t, kWide, true, C32><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (pl.full_table)  decode_lane_al_kernel<uint16_t, kWide, true, C32><<<grid, kLaneThreads, smem, s>>>(job);
+    else                     decode_lane_al_kernel<uint16_t, kWide, false, C32><<<grid, kLaneThreads, smem, s>>>(job);
+}
 void launch_encode_al(const Plan &pl, const LaneEncJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {
-    if (pl.cls == kNarrow)   encode_lane_al_kernel<uint16_t, kNarrow, true><<<grid, kLaneThreads, smem, s>>>(job);
-    else if (pl.wide_table)  encode_lane_al_kernel<uint32_t, kWide, true><<<grid, kLaneThreads, smem, s>>>(job);
-    else if (pl.full_table)  encode_lane_al_kernel<uint16_t, kWide, true><<<grid, kLaneThreads, smem, s>>>(job);
-    else                     encode_lane_al_kernel<uint16_t, kWide, false><<<grid, kLaneThreads, smem, s>>>(job);
+    if (pl.cls == kNarrow) encode_lane_al_kernel<uint16_t, kNarrow, true, false><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (pl.c == 32)   launch_encode_wide<true>(pl, job, grid, smem, s);
+    else                   launch_encode_wide<false>(pl, job, grid, smem, s);
 }
 void launch_decode_al(const Plan &pl, const LaneDecJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {
-    if (pl.cls == kNarrow)   decode_lane_al_kernel<uint16_t, kNarrow, true><<<grid, kLaneThreads, smem, s>>>(job);
-    else if (pl.wide_table)  decode_lane_al_kernel<uint32_t, kWide, true><<<grid, kLaneThreads, smem, s>>>(job);
-    else if (pl.full_table)  decode_lane_al_kernel<uint16_t, kWide, true><<<grid, kLaneThreads, smem, s>>>(job);
-    else                     decode_lane_al_kernel<uint16_t, kWide, false><<<grid, kLaneThreads, smem, s>>>(job);
+    if (pl.cls == kNarrow) decode_lane_al_kernel<uint16_t, kNarrow, true, false><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (pl.c == 32)   launch_decode_wide<true>(pl, job, grid, smem, s);
+    else                   launch_decode_wide<false>(pl, job, grid, smem, s);
 }
 
 void launch_encode_warp(int cls, const LaneEncJob &job, cudaStream_t s)
@@ -481,15 +503,15 @@ int encode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     job.slots = slots; job.slot_stride = pl.slot_stride;
     job.sizes = sizes; job.status = d_status;
     job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
-    job.one = pl.c <= 31 ? 1u << (32 - pl.c) : 0u;
+    job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
     const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
-    const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
+    const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2) + kTabPadBytes;
     {
         KernelTimer kt(ctx, device, s, REDUX_KERNEL_ENCODE);
         if (pl.warp)            launch_encode_warp(pl.cls, job, s);
         else if (pl.aligned)    launch_encode_al(pl, job, grid, smem, s);
-        else if (pl.wide_table) launch_encode<uint32_t>(pl.cls, job, grid, smem, s);
-        else                    launch_encode<uint16_t>(pl.cls, job, grid, smem, s);
+        else if (pl.wide_table) launch_encode<uint32_t>(job, grid, smem, s);
+        else                    launch_encode<uint16_t>(job, grid, smem, s);
     }
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
@@ -519,15 +541,15 @@ int decode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     job.comp = d_comp; job.comp_off = d_comp_off; job.n_blocks = n_blocks;
     job.raw = d_raw; job.raw_off = d_raw_off; job.raw_len = d_raw_lens; job.consumed = d_consumed;
     job.status = d_status; job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
-    job.one = pl.c <= 31 ? 1u << (32 - pl.c) : 0u;
+    job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
     const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
-    const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2);
+    const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2) + kTabPadBytes;
     {
         KernelTimer kt(ctx, device, s, REDUX_KERNEL_DECODE);
         if (pl.warp)            launch_decode_warp(pl.cls, job, s);
         else if (pl.aligned)    launch_decode_al(pl, job, grid, smem, s);
-        else if (pl.wide_table) launch_decode<uint32_t>(pl.cls, job, grid, smem, s);
-        else                    launch_decode<uint16_t>(pl.cls, job, grid, smem, s);
+        else if (pl.wide_table) launch_decode<uint32_t>(job, grid, smem, s);
+        else                    launch_decode<uint16_t>(job, grid, smem, s);
     }
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
@@ -646,14 +668,49 @@ std::vector<Shard> make_shards(uint64_t n_blocks, size_t n_dev)
     return s;
 }
 
-std::vector<Shard> make_chunks(uint64_t count)
+// tuning knobs (environment, read once): number of chunks per shard and of compute streams they rotate over
+int env_int(const char *name, int dflt, int lo, int hi)
 {
-    // at most kPipeStreams chunks (one stream each), whole CTAs, at least 8 CTAs each
-    uint64_t cb = (count + kPipeStreams - 1) / kPipeStreams;
-    cb = (cb + kLaneThreads - 1) / kLaneThreads * kLaneThreads;
-    cb = std::max<uint64_t>(cb, (uint64_t)kLaneThreads * 8);
+    const char *v = std::getenv(name);
+    if (!v) return dflt;
+    int x = std::atoi(v);
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+int pipe_chunks()  { static int v = env_int("REDUX_PIPE_CHUNKS", 20, 1, 256); return v; }
+int pipe_streams() { static int v = env_int("REDUX_PIPE_STREAMS", kPipeStreams, 1, kPipeStreams); return v; }
+
+// Cuts a shard into chunks of whole CTAs.  A lane needs the same ~10-25 ms for its block however few
+// blocks are in flight, so what a chunk's size controls is only WHEN its copy-in ends and its copy-out
+// can start.  ramp < 0: small chunks FIRST (decode: the device-to-host link is the bottleneck, so the
+// first decoded bytes must be ready as early as possible); ramp > 0: small chunks LAST (encode: the
+// host-to-device link is the bottleneck, so as little as possible may remain after the last byte lands).
+std::vector<Shard> make_chunks(uint64_t count, int ramp)
+{
+    const uint64_t cta = kLaneThreads;
+    const uint64_t ctas = (count + cta - 1) / cta;
+    std::vector<uint64_t> sizes;                                  // in CTAs
+    const uint64_t want = (uint64_t)pipe_chunks();
+    static const int ramp_on = env_int("REDUX_PIPE_RAMP", 1, 0, 1);
+    if (ramp != 0 && ramp_on && ctas >= 128) {
+        static const uint64_t steps[] = {4, 4, 8, 12, 16};
+        uint64_t used = 0;
+        for (uint64_t st : steps) { sizes.push_back(st); used += st; }
+        const uint64_t rest = ctas - used;
+        const uint64_t nrest = want > 5 ? want - 5 : 1;
+        const uint64_t per = (rest + nrest - 1) / nrest;
+        for (uint64_t a = 0; a < rest; a += per) sizes.push_back(std::min(per, rest - a));
+        if (ramp > 0) std::reverse(sizes.begin(), sizes.end());
+    } else {
+        uint64_t per = std::max<uint64_t>((ctas + want - 1) / want, 8);   // at least 8 CTAs each
+        for (uint64_t a = 0; a < ctas; a += per) sizes.push_back(std::min(per, ctas - a));
+    }
     std::vector<Shard> c;
-    for (uint64_t a = 0; a < count; a += cb) c.push_back({a, std::min(cb, count - a)});
+    uint64_t first = 0;
+    for (uint64_t sz : sizes) {
+        const uint64_t n = std::min(sz * cta, count - first);
+        if (n) c.push_back({first, n});
+        first += n;
+    }
     return c;
 }
 
@@ -735,7 +792,7 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
     pl.warp = choose_warp(ctx, sh.count);
-    res->chunks = make_chunks(sh.count);
+    res->chunks = make_chunks(sh.count, +1);
     const size_t nc = res->chunks.size();
     res->chunk_base.assign(nc, 0); res->chunk_total.assign(nc, 0);
     res->local_off.assign(sh.count + 1, 0);
@@ -774,7 +831,7 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     int32_t *h_status = (int32_t *)d->pin_status.p;
     for (size_t k = 0; k < nc; ++k) {
         const Shard c = res->chunks[k];
-        cudaStream_t s = d->pipe[k % kPipeStreams];
+        cudaStream_t s = d->pipe[k % pipe_streams()];
         rc = REDUX_OK;
         cudaError_t e = cudaSuccess;
         const uint64_t b0 = rel[c.first], b1 = rel[c.first + c.count];
@@ -914,7 +971,7 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
     pl.warp = choose_warp(ctx, sh.count);
-    const std::vector<Shard> chunks = make_chunks(sh.count);
+    const std::vector<Shard> chunks = make_chunks(sh.count, -1);
     const size_t nc = chunks.size();
     CU_TRY(ctx, d->st_in.reserve(cbytes + 32));
     CU_TRY(ctx, d->st_off.reserve(rel.size() * sizeof(uint64_t)));
@@ -938,7 +995,7 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     int32_t *h_status = (int32_t *)d->pin_status.p;
     for (size_t k = 0; k < nc; ++k) {
         const Shard c = chunks[k];
-        cudaStream_t s = d->pipe[k % kPipeStreams];
+        cudaStream_t s = d->pipe[k % pipe_streams()];
         rc = REDUX_OK;
         cudaError_t e = cudaSuccess;
         const uint64_t c0 = crel[c.first], c1 = crel[c.first + c.count];

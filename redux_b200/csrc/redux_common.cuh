@@ -158,7 +158,7 @@ RDX_HD Renorm<T> renorm(T low, T high, uint32_t c) {
 // SURVEY.md A.4).  Shared by the host front end (redux_capi.cu) and the test harness.
 struct LanePlan {
     int cls; uint32_t f, c, tcap; bool wide_table; uint32_t magic_len; uint64_t slot_stride;
-    bool aligned;     // c <= 31 with 32-bit state: the tuned kernels of redux_lane_al.cuh
+    bool aligned;     // c <= 32 (32-bit coder state): the tuned kernels of redux_lane_al.cuh
     bool full_table;  // table entries can hold the reference's tree values (lowbit + increments)
 };
 RDX_HD LanePlan lane_plan(uint32_t f, uint32_t c, uint64_t max_block_len) {
@@ -172,7 +172,7 @@ RDX_HD LanePlan lane_plan(uint32_t f, uint32_t c, uint64_t max_block_len) {
     pl.magic_len = (uint32_t)updates + 2;                      // positions 0..updates, +1 read-ahead
     const uint64_t bound = ((max_block_len + 1) * (uint64_t)c + 7) / 8;
     pl.slot_stride = ((bound + 15) & ~(uint64_t)15) + 16;
-    pl.aligned = pl.cls != kHuge && c <= 31;
+    pl.aligned = pl.cls != kHuge;
     pl.full_table = pl.wide_table || updates + 256 <= 65535;   // cum(i) <= 256 + updates must fit u16
     return pl;
 }

@@ -1,4 +1,4 @@
-// redux_lane_al.cuh -- the tuned lane kernels for code_bits <= 31 (32-bit coder state): one stream per
+// redux_lane_al.cuh -- the tuned lane kernels for code_bits <= 32 (32-bit coder state): one stream per
 // lane exactly as in redux_lane_codec.cuh (same table layout, same jobs, same bytes), with the
 // instruction count per symbol cut where profiles/r01_final_* showed the issue slots going:
 //   * LEFT-ALIGNED coder state.  low/high (src/codec.rs:11-24) live in the top c bits of a 32-bit
@@ -38,6 +38,23 @@ __device__ __forceinline__ uint32_t clz_nz(uint32_t x) {
 #endif
 }
 
+// clz that may see zero as one instruction: FLO.SH answers 0xFFFFFFFF for 0, which every CLAMPED shift
+// below treats like 32
+__device__ __forceinline__ uint32_t clz_sh(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return clz_nz(x);
+#else
+    return x ? (uint32_t)__builtin_clz(x) : 0xFFFFFFFFu;
+#endif
+}
+// x << n and "the top n bits of x" with n up to 32 (and beyond: clamped), one SHF each
+__device__ __forceinline__ uint32_t shl_c(uint32_t x, uint32_t n) { return __funnelshift_lc(0u, x, n); }
+__device__ __forceinline__ uint32_t top_bits(uint32_t x, uint32_t n) { return __funnelshift_lc(x, 0u, n); }
+// leading bits low and high share (E1/E2 count).  C32: code_bits == 32 leaves no spare low bits, so the
+// XOR can be zero (interval collapsed to one value) and the count must come out as exactly 32.
+template <bool C32>
+__device__ __forceinline__ uint32_t common_prefix(uint32_t x) { return C32 ? (uint32_t)clz32(x) : clz_nz(x); }
+
 // ------------------------------------------------------------------ Fenwick table, v2 access paths
 // Same lane-interleaved storage as LaneTable<TW>.  FULL: node i holds the reference's tree[i]
 // (lowbit(i) + increments); otherwise increments only (u16 entries that must survive 65,536 updates).
@@ -69,7 +86,7 @@ struct LaneTable2 : LaneTable<TW> {
         const uint32_t S = s << 5;
         const uint32_t bothmask = s & (s + 1);                 // set bits above the lowest zero bit
         const uint32_t q = ~s & 255u;                          // clear bits of s
-        const uint32_t levels = q ? (q ^ (1u << (31 - clz32(q)))) : 0u;   // minus the one that leads to node 256
+        const uint32_t levels = q ^ __funnelshift_rc(0x80000000u, 0u, clz_sh(q));   // minus the one that leads to node 256
         TW *a[8];
         uint32_t v[8];
 #pragma unroll
@@ -109,7 +126,8 @@ struct LaneTable2 : LaneTable<TW> {
             uint32_t u[8];
 #pragma unroll
             for (int k = 1; k < 8; ++k)                        // (s | (2^k - 1)) + 1 = (s & (0xFF << k)) + 2^k
-                if (levels & (1u << (k - 1))) u[k] = a[k][32 << k];
+                u[k] = a[k][32 << k];                          // unconditional: "node 256" is the row after
+                                                               // the warp's table (padded, kTabPadBytes)
             // node s+1 (the odd node for even s, the following even node for odd s; node 256 unstored)
             if (!last) { TW *p = odd ? pn : po; *p = (TW)((odd ? xn : xo) + 1u); }
 #pragma unroll
@@ -122,7 +140,7 @@ struct LaneTable2 : LaneTable<TW> {
     __device__ __forceinline__ void update(uint32_t s) {
         const uint32_t S = s << 5;
         const uint32_t q = ~s & 255u;
-        const uint32_t levels = q ? (q ^ (1u << (31 - clz32(q)))) : 0u;
+        const uint32_t levels = q ^ __funnelshift_rc(0x80000000u, 0u, clz_sh(q));
         TW *p0 = t + B::node_index((s + 1u) & 255u);
         TW *a[8];
         uint32_t u[8];
@@ -130,7 +148,7 @@ struct LaneTable2 : LaneTable<TW> {
 #pragma unroll
         for (int k = 1; k < 8; ++k) {
             a[k] = t + (S & (0x1FE0u << k)) + (32 << k);
-            if (levels & (1u << (k - 1))) u[k] = *a[k];
+            u[k] = *a[k];                                      // unconditional, see query<>
         }
         if (q) *p0 = (TW)(u0 + 1u);
 #pragma unroll
@@ -212,7 +230,7 @@ struct BitSink2 {
 
 // One coding step on left-aligned state (src/codec.rs:55-89).  L: low << sh, H: (high << sh) | ones.
 // Returns the number of shifts.
-template <int CLS>
+template <int CLS, bool C32>
 __device__ __forceinline__ uint32_t encode_step_al(uint32_t &L, uint32_t &H, uint32_t &pend, BitSink2 &sink,
                                                    uint32_t cl, uint32_t ch, uint32_t count,
                                                    const typename Cls<CLS>::M &g, uint32_t sh, uint32_t one)
@@ -224,17 +242,17 @@ __device__ __forceinline__ uint32_t encode_step_al(uint32_t &L, uint32_t &H, uin
     // `one` == 1 << sh, handed in as an opaque value so that quotient * one + L stays a single IMAD
     const uint32_t nh2 = ~((uint32_t)C::divc(nh, g, count) * one + (L - 1u));   // ~high' (:59)
     const uint32_t l2 = (uint32_t)C::divc(nl, g, count) * one + L;              // low'   (:60)
-    const uint32_t n1 = clz_nz(~(l2 ^ nh2));                       // E1/E2 shifts (:63-74)
-    const uint32_t k = clz_nz(~(((l2 & nh2) << 1) << n1));         // E3 shifts (:75-83)
-    const uint32_t n = n1 + k;                                     // <= c <= 31
-    pend = sink.put_code(__funnelshift_l(l2, 0u, n1), n1, pend, k);
-    L = (l2 << n) & 0x7FFFFFFFu;                                   // :87-88 after the E3 subtraction
-    H = ~(nh2 << n) | 0x80000000u;                                 // high refills with ones
+    const uint32_t n1 = common_prefix<C32>(~(l2 ^ nh2));           // E1/E2 shifts (:63-74)
+    const uint32_t k = clz_nz(~shl_c((l2 & nh2) << 1, n1));        // E3 shifts (:75-83); bit 0 of the operand is set
+    const uint32_t n = n1 + k;                                     // <= c
+    pend = sink.put_code(top_bits(l2, n1), n1, pend, k);
+    L = shl_c(l2, n) & 0x7FFFFFFFu;                                // :87-88 after the E3 subtraction
+    H = ~shl_c(nh2, n) | 0x80000000u;                              // high refills with ones
     return n;
 }
 
 // ------------------------------------------------------------------ encoder
-template <typename TW, int CLS, bool FULL>
+template <typename TW, int CLS, bool FULL, bool C32>
 __global__ void __launch_bounds__(kLaneThreads, 2)
 encode_lane_al_kernel(const LaneEncJob job)
 {
@@ -272,7 +290,7 @@ encode_lane_al_kernel(const LaneEncJob job)
         const uint32_t sym = src.next();
         uint32_t cl, ch;
         tab.template query<true>(sym, t, cl, ch);
-        encode_step_al<CLS>(L, H, pend, sink, cl, ch, kNsym + t, g, sh, one);
+        encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, kNsym + t, g, sh, one);
     }
     // frozen phase (adaptive_tree.rs:84): total == FMAX, table and reciprocal are constant
     const M gf = gn;                                       // = magic[n_adapt]
@@ -286,16 +304,16 @@ encode_lane_al_kernel(const LaneEncJob job)
         for (; t + 1 < len; ++t) {
             const uint32_t cl_cur = cl, ch_cur = ch;
             tab.query_frozen(src.next(), countf, cl, ch);
-            encode_step_al<CLS>(L, H, pend, sink, cl_cur, ch_cur, countf, gf, sh, one);
+            encode_step_al<CLS, C32>(L, H, pend, sink, cl_cur, ch_cur, countf, gf, sh, one);
         }
-        encode_step_al<CLS>(L, H, pend, sink, cl, ch, countf, gf, sh, one);
+        encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, countf, gf, sh, one);
         ++t;
     }
     // EOF symbol: cum(256) = total - 1, then the tail of src/codec.rs:91-99: the remaining `extra` MSBs of
     // low, the first of them carrying the pending run, then flush
-    const uint32_t shifts = encode_step_al<CLS>(L, H, pend, sink, countf - 1, countf, countf, gf, sh, one);
+    const uint32_t shifts = encode_step_al<CLS, C32>(L, H, pend, sink, countf - 1, countf, countf, gf, sh, one);
     const uint32_t extra = c - shifts;
-    sink.put_code(__funnelshift_l(L, 0u, extra), extra, pend, 0);
+    sink.put_code(top_bits(L, extra), extra, pend, 0);
     job.sizes[blk] = sink.finish();
     job.status[blk] = 0;
 }
@@ -328,14 +346,14 @@ struct BitWindow {
         return first;
     }
     __device__ __forceinline__ uint32_t win() const { return __funnelshift_l(w1, w0, pos); }
-    __device__ __forceinline__ void advance(uint32_t n) {                   // n <= 31
+    __device__ __forceinline__ void advance(uint32_t n) {                   // n <= 32
         pos += n;
         if (pos >= 32) { pos -= 32; w0 = w1; w1 = swap(nxt); nxt = ld(); }
     }
 };
 
 // ------------------------------------------------------------------ decoder
-template <typename TW, int CLS, bool FULL>
+template <typename TW, int CLS, bool FULL, bool C32>
 struct LaneDecoderAl {
     using C = Cls<CLS>;
     using P = typename C::P;
@@ -410,31 +428,31 @@ struct LaneDecoderAl {
             const uint32_t l2 = (uint32_t)C::divc(plo, g, count) * one + L;
             if (ADAPT && !PEEK) tab.update(sym);
             // src/codec.rs:140-158 in closed form
-            const uint32_t n1 = clz_nz(~(l2 ^ nh2));
-            const uint32_t k = clz_nz(~(((l2 & nh2) << 1) << n1));
+            const uint32_t n1 = common_prefix<C32>(~(l2 ^ nh2));
+            const uint32_t k = clz_nz(~shl_c((l2 & nh2) << 1, n1));
             const uint32_t n = n1 + k;
             if (n > left) { st = 1; left = 0; return; }           // Err(Eof) inside get_bit (:49-52)
             if (PEEK) { st = 6; return; }                         // a data symbol with nowhere to go
             left -= n;
             // E1/E2: shift the window, pulling the next stream bits in; E3: keep the MSB, drop k bits below it
             const uint32_t win = bw.win();
-            const uint32_t A = __funnelshift_l(win, V, n1);
-            const uint32_t Bv = __funnelshift_l(win << n1, A, k);
+            const uint32_t A = __funnelshift_lc(win, V, n1);
+            const uint32_t Bv = __funnelshift_lc(shl_c(win, n1), A, k);
             V = (A & 0x80000000u) | (Bv & 0x7FFFFFFFu);
             bw.advance(n);
-            L = (l2 << n) & 0x7FFFFFFFu;
-            H = ~(nh2 << n) | 0x80000000u;
+            L = shl_c(l2, n) & 0x7FFFFFFFu;
+            H = ~shl_c(nh2, n) | 0x80000000u;
             out.put(sym);
             ++t;
         }
     }
 };
 
-template <typename TW, int CLS, bool FULL>
+template <typename TW, int CLS, bool FULL, bool C32>
 __global__ void __launch_bounds__(kLaneThreads, 2)
 decode_lane_al_kernel(const LaneDecJob job)
 {
-    using D = LaneDecoderAl<TW, CLS, FULL>;
+    using D = LaneDecoderAl<TW, CLS, FULL, C32>;
     using M = typename D::M;
     extern __shared__ uint4 smem_u4[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -33,6 +33,8 @@ namespace rdx {
 constexpr int kLaneWarpsPerCta = 7;                 // 7 warps x 16 KiB tables; 2 CTAs per SM
 constexpr int kLaneThreads = kLaneWarpsPerCta * 32;
 constexpr int kTabNodes = 256;                      // nodes 0..255 (node 0 stays 0: the "absent" node)
+constexpr int kTabPadBytes = 128;                   // one row after the last warp's table: the tuned kernels load
+                                                    // the update path's "node 256" unconditionally (never stored)
 
 struct LaneEncJob {
     const uint8_t *in;          // raw bytes
@@ -45,7 +47,7 @@ struct LaneEncJob {
     const void *magic;          // Magic32/Magic64 [magic_len], entry tt <-> count 257+tt
     uint32_t f, c;
     uint32_t tcap;              // FMAX - NSYM: number of model updates before the freeze
-    uint32_t one;               // 1 << (32 - c) for c <= 31 (redux_lane_al.cuh), else 0
+    uint32_t one;               // 1 << (32 - c) for c <= 32 (redux_lane_al.cuh), else 0
 };
 
 struct LaneDecJob {

@@ -3,6 +3,7 @@ import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import redux_b200 as rb
+rb.lib()   # before CUDA initialises: the library's load hook asks for 32 hardware queues
 n, L = 65536, 65536
 ctx = rb.Context([0])
 model = rb.AdaptiveTreeModel(rb.Parameters(8, 14, 16))

@@ -12,7 +12,7 @@ thread_local EmuIdx threadIdx, blockIdx, blockDim, gridDim;
 
 namespace rdx {
 // dynamic shared memory of one CTA: 7 warps x 256 nodes x 32 lanes x 4 B
-uint4 smem_u4[kLaneWarpsPerCta * kTabNodes * 32 * 4 / 16];
+uint4 smem_u4[(kLaneWarpsPerCta * kTabNodes * 32 * 4 + kTabPadBytes) / 16];
 }
 
 using namespace rdx;
@@ -71,14 +71,15 @@ extern "C" int emu_encode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, i
     job.in = in; job.in_off = in_off; job.n_blocks = n_blocks;
     job.slots = slots; job.slot_stride = pl.slot_stride; job.sizes = sizes; job.status = status;
     job.magic = magic.data(); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
-    job.one = pl.c <= 31 ? 1u << (32 - pl.c) : 0u;
+    job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
 #define RUN(TW) \
     (pl.cls == kNarrow ? run_grid(encode_lane_kernel<TW, kNarrow>, job, n_blocks) : \
      pl.cls == kWide   ? run_grid(encode_lane_kernel<TW, kWide>, job, n_blocks)   : \
                          run_grid(encode_lane_kernel<TW, kHuge>, job, n_blocks))
 #define RUN_AL(TW, FULL) \
-    (pl.cls == kNarrow ? run_grid(encode_lane_al_kernel<TW, kNarrow, FULL>, job, n_blocks) : \
-                         run_grid(encode_lane_al_kernel<TW, kWide, FULL>, job, n_blocks))
+    (pl.cls == kNarrow ? run_grid(encode_lane_al_kernel<TW, kNarrow, FULL, false>, job, n_blocks) : \
+     pl.c == 32        ? run_grid(encode_lane_al_kernel<TW, kWide, FULL, true>, job, n_blocks) : \
+                         run_grid(encode_lane_al_kernel<TW, kWide, FULL, false>, job, n_blocks))
     if (pl.aligned && !legacy) {
         if (pl.wide_table) RUN_AL(uint32_t, true);
         else if (pl.full_table) RUN_AL(uint16_t, true);
@@ -103,14 +104,15 @@ extern "C" int emu_decode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, i
     job.comp = comp; job.comp_off = comp_off; job.n_blocks = n_blocks;
     job.raw = raw; job.raw_off = raw_off; job.raw_len = raw_len; job.consumed = consumed;
     job.status = status; job.magic = magic.data(); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
-    job.one = pl.c <= 31 ? 1u << (32 - pl.c) : 0u;
+    job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
 #define RUN(TW) \
     (pl.cls == kNarrow ? run_grid(decode_lane_kernel<TW, kNarrow>, job, n_blocks) : \
      pl.cls == kWide   ? run_grid(decode_lane_kernel<TW, kWide>, job, n_blocks)   : \
                          run_grid(decode_lane_kernel<TW, kHuge>, job, n_blocks))
 #define RUN_AL(TW, FULL) \
-    (pl.cls == kNarrow ? run_grid(decode_lane_al_kernel<TW, kNarrow, FULL>, job, n_blocks) : \
-                         run_grid(decode_lane_al_kernel<TW, kWide, FULL>, job, n_blocks))
+    (pl.cls == kNarrow ? run_grid(decode_lane_al_kernel<TW, kNarrow, FULL, false>, job, n_blocks) : \
+     pl.c == 32        ? run_grid(decode_lane_al_kernel<TW, kWide, FULL, true>, job, n_blocks) : \
+                         run_grid(decode_lane_al_kernel<TW, kWide, FULL, false>, job, n_blocks))
     if (pl.aligned && !legacy) {
         if (pl.wide_table) RUN_AL(uint32_t, true);
         else if (pl.full_table) RUN_AL(uint16_t, true);
@@ -119,4 +121,27 @@ extern "C" int emu_decode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, i
 #undef RUN
 #undef RUN_AL
     return 0;
+}
+
+// One coder step of the tuned kernels on an arbitrary (low, high) state, for the closed-form-vs-loop test.
+// Returns the shift count; *bits / *nbits = what the step appended to an empty packer (pending run 0 before).
+extern "C" uint32_t emu_step_al(uint32_t c, uint32_t f, uint32_t low, uint32_t high, uint32_t cl, uint32_t ch,
+                                uint32_t count, uint32_t *new_low, uint32_t *new_high, uint64_t *bits,
+                                uint32_t *nbits, uint32_t *pend_after)
+{
+    alignas(16) uint8_t slot[64] = {0};
+    BitSink2 sink;
+    sink.init(slot);
+    const uint32_t sh = 32 - c, one = 1u << sh;
+    uint32_t L = low << sh, H = (high << sh) | (one - 1u), pend = 0, n;
+    const Magic64 g = make_magic64(count, f + c);
+    if (c == 32) n = encode_step_al<kWide, true>(L, H, pend, sink, cl, ch, count, g, sh, one);
+    else         n = encode_step_al<kWide, false>(L, H, pend, sink, cl, ch, count, g, sh, one);
+    *new_low = L >> sh; *new_high = H >> sh;
+    // whole words already stored + the accumulator remainder
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < sink.wi; ++i) v = (v << 32) | __byte_perm(sink.w0[i], 0, 0x0123);
+    v = (v << sink.nb) | (sink.acc & ((sink.nb ? (1ull << sink.nb) : 1ull) - 1));
+    *bits = v; *nbits = sink.wi * 32 + sink.nb; *pend_after = pend;
+    return n;
 }

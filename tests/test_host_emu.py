@@ -178,3 +178,67 @@ def test_long_pending_runs(emu):
         assert emu_encode(emu, blocks, f, c) == want
         outs, raw_len, consumed, status = emu_decode(emu, want, [len(b) for b in blocks], f, c)
         assert (status == 0).all() and outs == blocks
+
+
+def _loop_step(c, low, high, cl, ch, count):
+    """src/codec.rs:58-89 as written: narrow, then the E1/E2/E3 loop with put_bit (pending run starts at 0)."""
+    half, q1, q3, mx = 2 << (c - 2), 1 << (c - 2), 3 << (c - 2), (1 << c) - 1
+    rng = high - low + 1
+    high = low + rng * ch // count - 1
+    low = low + rng * cl // count
+    out, pend, shifts = [], 0, 0
+    while True:
+        if high < half:
+            out += [0] + [1] * pend; pend = 0
+        elif low >= half:
+            out += [1] + [0] * pend; pend = 0
+        elif low >= q1 and high < q3:
+            pend += 1; low -= q1; high -= q1
+        else:
+            break
+        high = ((high << 1) + 1) & mx
+        low = (low << 1) & mx
+        shifts += 1
+    v = 0
+    for b in out:
+        v = (v << 1) | b
+    return low, high, shifts, v, len(out), pend
+
+
+def test_al_step_closed_form_equals_loop(emu):
+    """One coder step of the tuned kernels (left-aligned state, clamped shifts, FLO.SH counts) against the
+    reference's renormalisation loop on random and adversarial states: collapsed intervals (low == high
+    after narrowing, code_bits shifts), straddling states with long E3 runs, code_bits == 32."""
+    emu.emu_step_al.argtypes = [C.c_uint32] * 7 + [C.POINTER(C.c_uint32)] * 2 + [C.POINTER(C.c_uint64)] + [C.POINTER(C.c_uint32)] * 2
+    emu.emu_step_al.restype = C.c_uint32
+    rng = np.random.default_rng(2026)
+    for c, f in ((12, 10), (16, 14), (24, 22), (31, 20), (32, 30), (32, 12)):
+        q1, half, mx = 1 << (c - 2), 2 << (c - 2), (1 << c) - 1
+        fmax = (1 << f) - 1
+        cases = []
+        for i in range(3000):
+            kind = i % 4
+            if kind == 0:        # any legal state: low < half <= high or straddling quarters
+                low = int(rng.integers(0, half)); high = int(rng.integers(half, mx + 1))
+            elif kind == 1:      # narrowest legal range around the midpoint (long E3 runs)
+                low = half - q1 // 2 - int(rng.integers(1, 3)); high = low + q1 + int(rng.integers(1, 4))
+            elif kind == 2:      # tiny symbol widths: the narrowed interval collapses or nearly does
+                low = int(rng.integers(0, q1)); high = low + q1 + 1 + int(rng.integers(0, 3))
+            else:
+                low = 0; high = mx
+            high = min(high, mx)
+            if high - low + 1 < q1 + 2:
+                continue
+            count = int(rng.integers(257, fmax + 1)) if kind != 2 else fmax
+            cl = int(rng.integers(0, count)); ch = min(count, cl + (1 if kind == 2 else int(rng.integers(1, 40))))
+            cases.append((low, high, cl, ch, count))
+        collapsed = 0
+        for low, high, cl, ch, count in cases:
+            want = _loop_step(c, low, high, cl, ch, count)
+            nl, nh, pa, nb = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+            bits = C.c_uint64()
+            n = emu.emu_step_al(c, f, low, high, cl, ch, count, C.byref(nl), C.byref(nh), C.byref(bits), C.byref(nb), C.byref(pa))
+            got = (nl.value, nh.value, n, bits.value, nb.value, pa.value)
+            assert got == want, (c, f, low, high, cl, ch, count, got, want)
+            collapsed += want[2] == c
+        assert collapsed > 0 or f + 2 < c, "no collapsed interval exercised for (f,c)=(%d,%d)" % (f, c)
