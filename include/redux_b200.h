@@ -27,7 +27,7 @@ extern "C" {
 #define REDUX_INVALID_INPUT  2  /* Error::InvalidInput (src/model/mod.rs:64-65, src/bitio/mod.rs:79,149) */
 #define REDUX_IO_ERROR       3  /* Error::IoError */
 #define REDUX_CUDA_ERROR     4  /* CUDA runtime failure / no device; see redux_ctx_last_error() */
-#define REDUX_UNSUPPORTED    5  /* valid Parameters the device path does not implement (symbol_bits != 8) */
+#define REDUX_UNSUPPORTED    5  /* valid Parameters the device path does not implement (symbol_bits > 16) */
 #define REDUX_OUT_CAPACITY   6  /* an output buffer was too small (the streaming analogue is IoError) */
 
 /* ---- model kinds: which reference constructor the caller would have used */
@@ -70,6 +70,9 @@ const char *redux_error_string(int code);
 /* Upper bound of one compressed stream: (in_len+1 symbols) * code_bits bits, rounded up to bytes
  * (each coded symbol, EOF included, emits at most code_bits bits). */
 uint64_t redux_compress_bound(uint64_t in_len, uint32_t code_bits);
+/* The same for any symbol width: floor(8*in_len / symbol_bits) data symbols (a trailing partial symbol is
+ * dropped by the reference's reader, src/bitio/mod.rs:94-108 + src/codec.rs:106-110) plus EOF. */
+uint64_t redux_compress_bound_ex(uint64_t in_len, uint32_t symbol_bits, uint32_t code_bits);
 
 /* ---- context: owns per-device streams and workspaces. Not thread-safe (one caller at a time).
  * devices == NULL or n_devices <= 0: use the current device only. */
@@ -126,6 +129,22 @@ int redux_decode_batch(redux_ctx_t *ctx, int model_kind, const redux_params_t *p
                        const uint8_t *comp, const uint64_t *comp_offsets, uint64_t n_blocks,
                        uint8_t *raw, const uint64_t *raw_offsets, uint64_t *raw_lens,
                        uint64_t *consumed, int32_t *status);
+
+/* ---- pre-trained models.  The reference's compress()/decompress() take a Box<Model> (src/lib.rs:102,113)
+ * that the caller may have trained already through Model::get_frequency (src/model/mod.rs:23-25); the
+ * observable state of either model kind is its per-symbol frequency vector.  model_freq[symbol_count]
+ * (symbol_count = 2^symbol_bits + 1, EOF last; every entry >= 1, sum <= freq_max, else
+ * REDUX_INVALID_INPUT) is that vector; NULL = a fresh model.  Every block of the batch starts from it.
+ * Otherwise identical to redux_encode_batch / redux_decode_batch. */
+int redux_encode_batch_ex(redux_ctx_t *ctx, int model_kind, const redux_params_t *params,
+                          const uint32_t *model_freq,
+                          const uint8_t *in, const uint64_t *in_offsets, uint64_t n_blocks,
+                          uint8_t *out, uint64_t out_capacity, uint64_t *out_offsets, int32_t *status);
+int redux_decode_batch_ex(redux_ctx_t *ctx, int model_kind, const redux_params_t *params,
+                          const uint32_t *model_freq,
+                          const uint8_t *comp, const uint64_t *comp_offsets, uint64_t n_blocks,
+                          uint8_t *raw, const uint64_t *raw_offsets, uint64_t *raw_lens,
+                          uint64_t *consumed, int32_t *status);
 
 /* ---- batch, device-resident buffers (kernel-only timing; all pointers are device memory on
  * `device`, which must be one of the context's devices; work is enqueued on `stream` (a

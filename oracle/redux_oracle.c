@@ -424,7 +424,11 @@ size_t oracle_compress_bound(size_t in_len, uint64_t symbol_bits, uint64_t code_
     return (nsym * (size_t)code_bits + 7) / 8;
 }
 
+/* n_train > 0: the caller trains the Box<Model> before handing it over, exactly as a user of the
+ * reference can: Model::get_frequency(symbol) looks up AND updates (src/model/mod.rs:23-25), and
+ * compress()/decompress() accept whatever model they are given (src/lib.rs:102,113). */
 static int run(int decode, int kind, uint64_t s, uint64_t f, uint64_t cb,
+               const uint64_t *train, size_t n_train,
                const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap,
                uint64_t *in_count, uint64_t *out_count)
 {
@@ -433,6 +437,10 @@ static int run(int decode, int kind, uint64_t s, uint64_t f, uint64_t cb,
     if (e) { if (in_count) *in_count = 0; if (out_count) *out_count = 0; return e; }
     oracle_model *m = oracle_model_new(kind, &p);
     if (!m) return ORACLE_IO_ERROR;
+    for (size_t i = 0; i < n_train; i++) {
+        uint64_t lo, hi;
+        if ((e = oracle_model_get_frequency(m, train[i], &lo, &hi))) { oracle_model_free(m); return e; }
+    }
     codec c;
     codec_new(&c, m);                                             /* lib.rs:103 / :114 */
     struct oracle_bitreader r = {0, 0, 0, in, in_len};            /* lib.rs:104 */
@@ -447,13 +455,27 @@ static int run(int decode, int kind, uint64_t s, uint64_t f, uint64_t cb,
 int oracle_compress(int kind, uint64_t s, uint64_t f, uint64_t c, const uint8_t *in, size_t in_len,
                     uint8_t *out, size_t out_cap, uint64_t *in_count, uint64_t *out_count)
 {
-    return run(0, kind, s, f, c, in, in_len, out, out_cap, in_count, out_count);
+    return run(0, kind, s, f, c, NULL, 0, in, in_len, out, out_cap, in_count, out_count);
 }
 
 int oracle_decompress(int kind, uint64_t s, uint64_t f, uint64_t c, const uint8_t *in, size_t in_len,
                       uint8_t *out, size_t out_cap, uint64_t *in_count, uint64_t *out_count)
 {
-    return run(1, kind, s, f, c, in, in_len, out, out_cap, in_count, out_count);
+    return run(1, kind, s, f, c, NULL, 0, in, in_len, out, out_cap, in_count, out_count);
+}
+
+int oracle_compress_trained(int kind, uint64_t s, uint64_t f, uint64_t c, const uint64_t *train, size_t n_train,
+                            const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap,
+                            uint64_t *in_count, uint64_t *out_count)
+{
+    return run(0, kind, s, f, c, train, n_train, in, in_len, out, out_cap, in_count, out_count);
+}
+
+int oracle_decompress_trained(int kind, uint64_t s, uint64_t f, uint64_t c, const uint64_t *train, size_t n_train,
+                              const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap,
+                              uint64_t *in_count, uint64_t *out_count)
+{
+    return run(1, kind, s, f, c, train, n_train, in, in_len, out, out_cap, in_count, out_count);
 }
 
 /* ------------------------------------------------- CPU baseline batch driver */
@@ -472,7 +494,7 @@ static void *batch_worker(void *arg)
         uint64_t i = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
         if (i >= j->n) break;
         uint64_t ic = 0, oc = 0;
-        int e = run(j->decode, j->kind, j->s, j->f, j->c,
+        int e = run(j->decode, j->kind, j->s, j->f, j->c, NULL, 0,
                     j->in + j->in_off[i], (size_t)(j->in_off[i + 1] - j->in_off[i]),
                     j->out + j->out_off[i], (size_t)(j->out_off[i + 1] - j->out_off[i]), &ic, &oc);
         j->out_len[i] = oc;

@@ -89,6 +89,17 @@ int oracle_decompress(int kind, uint64_t symbol_bits, uint64_t freq_bits, uint64
                       const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap,
                       uint64_t *in_count, uint64_t *out_count);
 
+/* The same with a model the caller trained first: get_frequency(train[i]) for i < n_train on the fresh
+ * model (Model::get_frequency updates, src/model/mod.rs:23-25), then compress / decompress with it. */
+int oracle_compress_trained(int kind, uint64_t symbol_bits, uint64_t freq_bits, uint64_t code_bits,
+                            const uint64_t *train, size_t n_train,
+                            const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap,
+                            uint64_t *in_count, uint64_t *out_count);
+int oracle_decompress_trained(int kind, uint64_t symbol_bits, uint64_t freq_bits, uint64_t code_bits,
+                              const uint64_t *train, size_t n_train,
+                              const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap,
+                              uint64_t *in_count, uint64_t *out_count);
+
 /* Upper bound of compress() output: every coded symbol (incl. EOF) emits at most code_bits bits
  * (SURVEY.md A.4). */
 size_t oracle_compress_bound(size_t in_len, uint64_t symbol_bits, uint64_t code_bits);

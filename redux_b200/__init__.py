@@ -103,6 +103,8 @@ def lib():
     L.redux_error_string.restype = C.c_char_p
     L.redux_compress_bound.argtypes = [u64, u32]
     L.redux_compress_bound.restype = u64
+    L.redux_compress_bound_ex.argtypes = [u64, u32, u32]
+    L.redux_compress_bound_ex.restype = u64
     L.redux_ctx_create.argtypes = [C.POINTER(C.c_int), i32, C.POINTER(vp)]
     L.redux_ctx_destroy.argtypes = [vp]
     L.redux_ctx_destroy.restype = None
@@ -119,6 +121,8 @@ def lib():
         getattr(L, name).argtypes = [vp, i32, pp, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     L.redux_encode_batch.argtypes = [vp, i32, pp, vp, vp, u64, vp, u64, vp, vp]
     L.redux_decode_batch.argtypes = [vp, i32, pp, vp, vp, u64, vp, vp, vp, vp, vp]
+    L.redux_encode_batch_ex.argtypes = [vp, i32, pp, vp, vp, vp, u64, vp, u64, vp, vp]
+    L.redux_decode_batch_ex.argtypes = [vp, i32, pp, vp, vp, vp, u64, vp, vp, vp, vp, vp]
     L.redux_encode_batch_device.argtypes = [vp, i32, vp, i32, pp, vp, vp, u64, u64, vp, u64, vp, vp]
     L.redux_decode_batch_device.argtypes = [vp, i32, vp, i32, pp, vp, vp, u64, u64, vp, vp, vp, vp, vp]
     L.redux_generate_blocks_device.argtypes = [vp, i32, vp, vp, u64, u64, u64, u64]
@@ -146,8 +150,8 @@ def _raise(code, ctx=None):
     raise _ERRORS.get(code, ReduxError)(msg)
 
 
-def compress_bound(in_len, code_bits):
-    return int(lib().redux_compress_bound(in_len, code_bits))
+def compress_bound(in_len, code_bits, symbol_bits=8):
+    return int(lib().redux_compress_bound_ex(in_len, symbol_bits, code_bits))
 
 
 # --------------------------------------------------------------------------- Parameters / models
@@ -175,14 +179,18 @@ class Parameters:
 
 
 class Model:
-    """A fresh adaptive model handed to compress()/decompress(); consumed by the call like the
-    reference's ``Box<Model>`` (src/lib.rs:102)."""
+    """An adaptive model handed to compress()/decompress(); consumed by the call like the reference's
+    ``Box<Model>`` (src/lib.rs:102).  Fresh unless the caller trained it first: like the reference's trait
+    object it can be trained through ``get_frequency(symbol)``, which looks the symbol up AND counts it
+    (src/model/mod.rs:23-25); the coder then starts every stream from that state.  The state is plain
+    bookkeeping (one counter per symbol) kept on the host; all coding happens on the device."""
     kind = None
 
     def __init__(self, parameters):
         if not isinstance(parameters, Parameters):
             parameters = Parameters(*parameters)
         self.params = parameters
+        self.freq = None            # None = fresh (every symbol once); else uint32[symbol_count]
 
     def parameters(self):
         return self.params
@@ -190,6 +198,44 @@ class Model:
     @classmethod
     def new(cls, parameters):
         return cls(parameters)
+
+    def _state(self):
+        if self.freq is None:
+            self.freq = np.ones(self.params.symbol_count, dtype=np.uint32)
+        return self.freq
+
+    def total_frequency(self):
+        """Model::total_frequency (adaptive_tree.rs:100-103 / adaptive_linear.rs:47-49)."""
+        return int(self.params.symbol_count if self.freq is None else self.freq.sum())
+
+    def get_frequency(self, symbol):
+        """Model::get_frequency (adaptive_tree.rs:105-113 / adaptive_linear.rs:51-59): the symbol's
+        cumulative range BEFORE the update, then the update -- frozen once the total reaches freq_max."""
+        if symbol > self.params.symbol_eof:
+            raise InvalidInput("Invalid data found while processing input")
+        fr = self._state()
+        lo = int(fr[:symbol].sum())
+        hi = lo + int(fr[symbol])
+        if int(fr.sum()) < self.params.freq_max:
+            fr[symbol] += 1
+        return lo, hi
+
+    def train(self, symbols):
+        """get_frequency() for every symbol of an iterable (vectorised; same freeze rule)."""
+        fr = self._state()
+        room = self.params.freq_max - int(fr.sum())
+        sy = np.asarray(list(symbols) if not isinstance(symbols, np.ndarray) else symbols, dtype=np.int64)
+        if sy.size and (sy.min() < 0 or sy.max() > self.params.symbol_eof):
+            raise InvalidInput("Invalid data found while processing input")
+        sy = sy[:max(room, 0)]
+        np.add.at(fr, sy, 1)
+        return self
+
+    def _freq_ptr(self):
+        if self.freq is None:
+            return None
+        self.freq = np.ascontiguousarray(self.freq, dtype=np.uint32)
+        return self.freq.ctypes.data
 
 
 class AdaptiveLinearModel(Model):
@@ -274,10 +320,20 @@ class Context:
     def compress(self, data, model, out_capacity=None):
         """bytes -> (compressed bytes, (in_count, out_count)); redux::compress (src/lib.rs:102-109)."""
         a = np.frombuffer(bytes(data), dtype=np.uint8)
-        cap = out_capacity if out_capacity is not None else compress_bound(a.size, model.params.code_bits)
+        cap = out_capacity if out_capacity is not None else compress_bound(a.size, model.params.code_bits,
+                                                                           model.params.symbol_bits)
         out = np.empty(max(cap, 1), dtype=np.uint8)
-        ic, oc = C.c_uint64(), C.c_uint64()
         pc = model.params._c()
+        if model.freq is not None:
+            off = np.array([0, a.size], dtype=np.uint64)
+            out_off = np.zeros(2, dtype=np.uint64)
+            st = np.zeros(1, dtype=np.int32)
+            rc = lib().redux_encode_batch_ex(self._h, model.kind, C.byref(pc), model._freq_ptr(),
+                                             a.ctypes.data if a.size else None, _ptr(off), 1, out.ctypes.data, cap,
+                                             _ptr(out_off), _ptr(st))
+            _raise(rc, self)
+            return out[:int(out_off[1])].tobytes(), (a.size, int(out_off[1]))
+        ic, oc = C.c_uint64(), C.c_uint64()
         rc = lib().redux_compress(self._h, model.kind, C.byref(pc), a.ctypes.data if a.size else None, a.size,
                                   out.ctypes.data, cap, C.byref(ic), C.byref(oc))
         _raise(rc, self)
@@ -287,16 +343,27 @@ class Context:
         """bytes -> (raw bytes, (in_count, out_count)); redux::decompress (src/lib.rs:113-120)."""
         a = np.frombuffer(bytes(data), dtype=np.uint8)
         out = np.empty(max(out_capacity, 1), dtype=np.uint8)
-        ic, oc = C.c_uint64(), C.c_uint64()
         pc = model.params._c()
-        rc = lib().redux_decompress(self._h, model.kind, C.byref(pc), a.ctypes.data if a.size else None, a.size,
-                                    out.ctypes.data, out_capacity, C.byref(ic), C.byref(oc))
+        if model.freq is not None:
+            coff = np.array([0, a.size], dtype=np.uint64)
+            roff = np.array([0, out_capacity], dtype=np.uint64)
+            rl, cons = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
+            st = np.zeros(1, dtype=np.int32)
+            rc = lib().redux_decode_batch_ex(self._h, model.kind, C.byref(pc), model._freq_ptr(),
+                                             a.ctypes.data if a.size else None, _ptr(coff), 1, out.ctypes.data,
+                                             _ptr(roff), _ptr(rl), _ptr(cons), _ptr(st))
+            icv, ocv = int(cons[0]), int(rl[0])
+        else:
+            ic, oc = C.c_uint64(), C.c_uint64()
+            rc = lib().redux_decompress(self._h, model.kind, C.byref(pc), a.ctypes.data if a.size else None, a.size,
+                                        out.ctypes.data, out_capacity, C.byref(ic), C.byref(oc))
+            icv, ocv = ic.value, oc.value
         if rc not in (OK,):
             err = _ERRORS.get(rc, ReduxError)(lib().redux_error_string(rc).decode())
-            err.partial = out[:oc.value].tobytes()
-            err.counts = (ic.value, oc.value)
+            err.partial = out[:ocv].tobytes()
+            err.counts = (icv, ocv)
             raise err
-        return out[:oc.value].tobytes(), (ic.value, oc.value)
+        return out[:ocv].tobytes(), (icv, ocv)
 
     # ---- batch, host buffers
     def encode_batch(self, data, offsets, model, out=None, check=True):
@@ -306,13 +373,14 @@ class Context:
         n = offsets.size - 1
         if out is None:
             lens = offsets[1:] - offsets[:-1]
-            cap = int(((lens + np.uint64(1)) * np.uint64(model.params.code_bits) + np.uint64(7)).sum() // 8) + 8 * n
+            nsym = lens * np.uint64(8) // np.uint64(model.params.symbol_bits) + np.uint64(1)
+            cap = int((nsym * np.uint64(model.params.code_bits) + np.uint64(7)).sum() // 8) + 8 * n
             out = np.empty(max(cap, 1), dtype=np.uint8)
         out_off = np.zeros(n + 1, dtype=np.uint64)
         status = np.zeros(max(n, 1), dtype=np.int32)
         pc = model.params._c()
-        rc = lib().redux_encode_batch(self._h, model.kind, C.byref(pc), _ptr(data), _ptr(offsets), n,
-                                      _ptr(out), out.size, _ptr(out_off), _ptr(status))
+        rc = lib().redux_encode_batch_ex(self._h, model.kind, C.byref(pc), model._freq_ptr(), _ptr(data),
+                                         _ptr(offsets), n, _ptr(out), out.size, _ptr(out_off), _ptr(status))
         if check:
             _raise(rc, self)
         return out[:int(out_off[n])], out_off, status[:n]
@@ -329,8 +397,9 @@ class Context:
         consumed = np.zeros(max(n, 1), dtype=np.uint64)
         status = np.zeros(max(n, 1), dtype=np.int32)
         pc = model.params._c()
-        rc = lib().redux_decode_batch(self._h, model.kind, C.byref(pc), _ptr(comp), _ptr(comp_offsets), n,
-                                      _ptr(raw), _ptr(raw_offsets), _ptr(raw_lens), _ptr(consumed), _ptr(status))
+        rc = lib().redux_decode_batch_ex(self._h, model.kind, C.byref(pc), model._freq_ptr(), _ptr(comp),
+                                         _ptr(comp_offsets), n, _ptr(raw), _ptr(raw_offsets), _ptr(raw_lens),
+                                         _ptr(consumed), _ptr(status))
         if check:
             _raise(rc, self)
         return raw, raw_lens[:n], consumed[:n], status[:n]

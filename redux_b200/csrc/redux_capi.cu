@@ -20,6 +20,7 @@
 #include "redux_common.cuh"
 #include "redux_lane_codec.cuh"
 #include "redux_lane_al.cuh"
+#include "redux_generic_codec.cuh"
 #include "redux_warp_codec.cuh"
 
 using namespace rdx;
@@ -78,6 +79,7 @@ struct DeviceState {
     HostBuf pin_off, pin_status, pin_aux0, pin_aux1;
     DevBuf slots, sizes, flag;                 // encoder workspace
     DevBuf st_in, st_off, st_out, st_ooff, st_status, st_aux0, st_aux1, st_roff;   // host-API staging
+    DevBuf gen_tabs, gen_init, gen_freq;       // generic path: Fenwick columns, start tree, uploaded frequencies
     uint8_t *text_lut = nullptr;
     std::vector<MagicEntry> magics;
     bool smem_set = false;
@@ -93,6 +95,7 @@ struct redux_ctx {
     std::string last_error;
     uint64_t launches = 0;
     bool timing = false;                  // bracket every kernel with CUDA events (bench.py)
+    const uint32_t *model_freq = nullptr;  // pre-trained start state of the running *_ex call (host pointer)
     std::vector<TimedSpan> spans;
 };
 
@@ -152,6 +155,9 @@ cudaError_t configure_kernels()
 struct Plan {
     int cls; uint32_t f, c, tcap; bool wide_table; uint32_t magic_len; uint64_t slot_stride;
     bool aligned = false, full_table = false;   // see LanePlan
+    // generic path (redux_generic_codec.cuh): symbol_bits != 8 or a pre-trained model
+    bool generic = false; uint32_t s = 8, gen_threads = 0, gen_total = 0;
+    uint32_t *gen_tabs = nullptr; const uint32_t *gen_init = nullptr;
     bool warp = false;      // one stream per warp (latency mapping) instead of one per lane
 };
 
@@ -173,10 +179,20 @@ int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, P
     if (!p) return fail(ctx, REDUX_INVALID_INPUT, "params is NULL");
     if (!params_valid(p->symbol_bits, p->freq_bits, p->code_bits))
         return fail(ctx, REDUX_INVALID_INPUT, "Parameters::new rejects these parameters");
-    if (p->symbol_bits != (uint32_t)kSymbolBits)
-        return fail(ctx, REDUX_UNSUPPORTED, "device path implements symbol_bits == 8 only");
+    if (p->symbol_bits > kGenericMaxSymbolBits)
+        return fail(ctx, REDUX_UNSUPPORTED, "device path implements symbol_bits <= 16");
     if (max_block_len > 0xFFFFFFF0ull)
         return fail(ctx, REDUX_UNSUPPORTED, "blocks longer than 2^32-16 bytes are not supported");
+    pl->s = p->symbol_bits;
+    pl->generic = p->symbol_bits != (uint32_t)kSymbolBits || ctx->model_freq != nullptr;
+    if (pl->generic) {
+        // worst case: every coded symbol (floor(8 len / s) data symbols + EOF) emits code_bits bits
+        pl->f = p->freq_bits; pl->c = p->code_bits; pl->cls = kHuge; pl->tcap = 0; pl->wide_table = true;
+        pl->magic_len = 0;
+        const uint64_t bound = redux_compress_bound_ex(max_block_len, p->symbol_bits, p->code_bits);
+        pl->slot_stride = ((bound + 15) & ~(uint64_t)15) + 16;
+        return REDUX_OK;
+    }
     const LanePlan lp = lane_plan(p->freq_bits, p->code_bits, max_block_len);
     pl->f = lp.f; pl->c = lp.c; pl->cls = lp.cls; pl->tcap = lp.tcap; pl->wide_table = lp.wide_table;
     pl->magic_len = lp.magic_len; pl->slot_stride = lp.slot_stride;
@@ -187,7 +203,7 @@ int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, P
 int get_magic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const Plan &pl, const void **out)
 {
     *out = nullptr;
-    if (pl.cls == kHuge) return REDUX_OK;
+    if (pl.cls == kHuge || pl.generic) return REDUX_OK;
     const uint32_t nbits = pl.f + pl.c;
     for (auto &m : d->magics)
         if (m.cls == pl.cls && m.nbits == nbits && m.len >= pl.magic_len) { *out = m.ptr; return REDUX_OK; }
@@ -205,6 +221,52 @@ int get_magic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const Plan &p
     d->magics.push_back({pl.cls, nbits, len, ptr});
     *out = ptr;
     return REDUX_OK;
+}
+
+// Generic path set-up: uploads the start frequencies (if any), builds the start tree on the device and
+// sizes the per-thread Fenwick columns.  At most ~2 GB of columns; a thread codes several blocks in turn.
+int prepare_generic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const redux_params_t *p, uint64_t n_blocks, Plan *pl)
+{
+    if (!pl->generic) return REDUX_OK;
+    const uint32_t nsym = (1u << p->symbol_bits) + 1;
+    const uint64_t fmax = ((uint64_t)1 << p->freq_bits) - 1;
+    uint64_t total = nsym;
+    const uint32_t *d_freq = nullptr;
+    if (ctx->model_freq) {
+        total = 0;
+        for (uint32_t i = 0; i < nsym; ++i) {
+            if (ctx->model_freq[i] < 1) return fail(ctx, REDUX_INVALID_INPUT, "model frequency below 1");
+            total += ctx->model_freq[i];
+        }
+        // a reference model starts at symbol_count and stops growing at freq_max (adaptive_tree.rs:84)
+        if (total > fmax) return fail(ctx, REDUX_INVALID_INPUT, "model total exceeds freq_max");
+        CU_TRY(ctx, d->gen_freq.reserve(nsym * sizeof(uint32_t)));
+        CU_TRY(ctx, cudaMemcpyAsync(d->gen_freq.p, ctx->model_freq, nsym * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        d_freq = (const uint32_t *)d->gen_freq.p;
+    }
+    CU_TRY(ctx, d->gen_init.reserve((nsym + 1) * sizeof(uint32_t)));
+    build_tree_kernel<<<(nsym + 1 + 255) / 256, 256, 0, stream>>>(d_freq, nsym, (uint32_t *)d->gen_init.p);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    const uint64_t col_bytes = (uint64_t)(nsym + 1) * sizeof(uint32_t);
+    uint64_t threads = std::min<uint64_t>((n_blocks + kGenericThreads - 1) / kGenericThreads * kGenericThreads,
+                                          (uint64_t)148 * 16 * kGenericThreads);
+    const uint64_t budget = (uint64_t)2 << 30;
+    if (threads * col_bytes > budget) threads = std::max<uint64_t>(budget / col_bytes / kGenericThreads, 1) * kGenericThreads;
+    CU_TRY(ctx, d->gen_tabs.reserve(threads * col_bytes));
+    // the start tree must be complete before kernels on other streams read it; the upload buffer is reused
+    CU_TRY(ctx, cudaStreamSynchronize(stream));
+    pl->gen_threads = (uint32_t)threads; pl->gen_total = (uint32_t)total;
+    pl->gen_tabs = (uint32_t *)d->gen_tabs.p; pl->gen_init = (const uint32_t *)d->gen_init.p;
+    return REDUX_OK;
+}
+
+GenericJob generic_job(const Plan &pl)
+{
+    GenericJob g{};
+    g.tabs = pl.gen_tabs; g.init_tree = pl.gen_init; g.init_total = pl.gen_total;
+    g.s = pl.s; g.f = pl.f; g.c = pl.c; g.n_threads = pl.gen_threads;
+    return g;
 }
 
 // code_bits > 32: the generic kernels
@@ -313,7 +375,7 @@ extern "C" int redux_parameters_new(uint32_t s, uint32_t f, uint32_t c, redux_pa
 extern "C" int redux_params_supported(const redux_params_t *p)
 {
     if (!p || !params_valid(p->symbol_bits, p->freq_bits, p->code_bits)) return REDUX_INVALID_INPUT;
-    return p->symbol_bits == (uint32_t)kSymbolBits ? REDUX_OK : REDUX_UNSUPPORTED;
+    return p->symbol_bits <= kGenericMaxSymbolBits ? REDUX_OK : REDUX_UNSUPPORTED;
 }
 
 extern "C" const char *redux_error_string(int code)
@@ -333,6 +395,12 @@ extern "C" const char *redux_error_string(int code)
 extern "C" uint64_t redux_compress_bound(uint64_t in_len, uint32_t code_bits)
 {
     return ((in_len + 1) * (uint64_t)code_bits + 7) / 8;
+}
+
+extern "C" uint64_t redux_compress_bound_ex(uint64_t in_len, uint32_t symbol_bits, uint32_t code_bits)
+{
+    if (symbol_bits == 0) return 0;
+    return ((in_len * 8 / symbol_bits + 1) * (uint64_t)code_bits + 7) / 8;
 }
 
 extern "C" int redux_debug_magic(uint64_t d, uint32_t nbits, int wide, uint64_t *magic, uint32_t *shift)
@@ -436,7 +504,7 @@ extern "C" void redux_ctx_destroy(redux_ctx_t *ctx)
         for (int i = 0; i < kPipeStreams; ++i) if (d.pipe[i]) cudaStreamDestroy(d.pipe[i]);
         for (HostBuf *b : {&d.pin_off, &d.pin_status, &d.pin_aux0, &d.pin_aux1}) b->release();
         for (DevBuf *b : {&d.slots, &d.sizes, &d.flag, &d.st_in, &d.st_off, &d.st_out, &d.st_ooff,
-                          &d.st_status, &d.st_aux0, &d.st_aux1, &d.st_roff}) b->release();
+                          &d.st_status, &d.st_aux0, &d.st_aux1, &d.st_roff, &d.gen_tabs, &d.gen_init, &d.gen_freq}) b->release();
         for (auto &m : d.magics) cudaFree(m.ptr);
         if (d.text_lut) cudaFree(d.text_lut);
     }
@@ -508,7 +576,13 @@ int encode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2) + kTabPadBytes;
     {
         KernelTimer kt(ctx, device, s, REDUX_KERNEL_ENCODE);
-        if (pl.warp)            launch_encode_warp(pl.cls, job, s);
+        if (pl.generic) {
+            GenericJob g = generic_job(pl);
+            g.in = d_in; g.in_off = d_in_off; g.n_blocks = n_blocks;
+            g.slots = slots; g.slot_stride = pl.slot_stride; g.sizes = sizes; g.status = d_status;
+            encode_generic_kernel<<<pl.gen_threads / kGenericThreads, kGenericThreads, 0, s>>>(g);
+        }
+        else if (pl.warp)       launch_encode_warp(pl.cls, job, s);
         else if (pl.aligned)    launch_encode_al(pl, job, grid, smem, s);
         else if (pl.wide_table) launch_encode<uint32_t>(job, grid, smem, s);
         else                    launch_encode<uint16_t>(job, grid, smem, s);
@@ -546,7 +620,13 @@ int decode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2) + kTabPadBytes;
     {
         KernelTimer kt(ctx, device, s, REDUX_KERNEL_DECODE);
-        if (pl.warp)            launch_decode_warp(pl.cls, job, s);
+        if (pl.generic) {
+            GenericJob g = generic_job(pl);
+            g.in = d_comp; g.in_off = d_comp_off; g.n_blocks = n_blocks;
+            g.raw = d_raw; g.raw_off = d_raw_off; g.raw_len = d_raw_lens; g.consumed = d_consumed; g.status = d_status;
+            decode_generic_kernel<<<pl.gen_threads / kGenericThreads, kGenericThreads, 0, s>>>(g);
+        }
+        else if (pl.warp)       launch_decode_warp(pl.cls, job, s);
         else if (pl.aligned)    launch_decode_al(pl, job, grid, smem, s);
         else if (pl.wide_table) launch_decode<uint32_t>(job, grid, smem, s);
         else                    launch_decode<uint16_t>(job, grid, smem, s);
@@ -569,7 +649,7 @@ extern "C" int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *str
     if ((rc = check_kind(ctx, model_kind))) return rc;
     Plan pl;
     if ((rc = make_plan(ctx, params, max_block_len, &pl))) return rc;
-    pl.warp = choose_warp(ctx, n_blocks);
+    pl.warp = !pl.generic && choose_warp(ctx, n_blocks);
     DeviceState *d = find_dev(ctx, device);
     if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
     if (!d_in_offsets || !d_out_offsets || !d_status || (!d_out && out_capacity))
@@ -581,6 +661,7 @@ extern "C" int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *str
 
     const void *magic = nullptr;
     if ((rc = get_magic(ctx, d, s, pl, &magic))) return rc;
+    if ((rc = prepare_generic(ctx, d, s, params, n_blocks, &pl))) return rc;
     CU_TRY(ctx, d->slots.reserve(n_blocks * pl.slot_stride));
     CU_TRY(ctx, d->sizes.reserve(n_blocks * sizeof(uint32_t)));
     CU_TRY(ctx, d->flag.reserve(sizeof(int32_t)));
@@ -601,7 +682,7 @@ extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *str
     if ((rc = check_kind(ctx, model_kind))) return rc;
     Plan pl;
     if ((rc = make_plan(ctx, params, max_block_len, &pl))) return rc;
-    pl.warp = choose_warp(ctx, n_blocks);
+    pl.warp = !pl.generic && choose_warp(ctx, n_blocks);
     DeviceState *d = find_dev(ctx, device);
     if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
     if (n_blocks == 0) return REDUX_OK;
@@ -611,6 +692,7 @@ extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *str
     cudaStream_t s = (cudaStream_t)stream_;   // NULL = the default stream, as in CUDA
     const void *magic = nullptr;
     if ((rc = get_magic(ctx, d, s, pl, &magic))) return rc;
+    if ((rc = prepare_generic(ctx, d, s, params, n_blocks, &pl))) return rc;
     return decode_launch(ctx, device, s, pl, magic, d_comp, d_comp_offsets, n_blocks, d_raw, d_raw_offsets,
                          d_raw_lens, d_consumed, d_status);
 }
@@ -736,7 +818,7 @@ void for_each_device(redux_ctx *ctx, size_t nd, std::vector<int> &rcs, F fn)
     std::vector<uint64_t> launches(nd, 0);
     std::vector<std::vector<TimedSpan>> spans(nd);
     for (size_t g = 0; g < nd; ++g) th.emplace_back([&, g] {
-        redux_ctx view; view.sched = ctx->sched; view.timing = ctx->timing;
+        redux_ctx view; view.sched = ctx->sched; view.timing = ctx->timing; view.model_freq = ctx->model_freq;
         view.devs.push_back(ctx->devs[g]);
         rcs[g] = fn(&view, &view.devs[0], g);
         ctx->devs[g] = view.devs[0];          // workspaces may have grown
@@ -791,8 +873,9 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     Plan pl;
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
-    pl.warp = choose_warp(ctx, sh.count);
-    res->chunks = make_chunks(sh.count, +1);
+    pl.warp = !pl.generic && choose_warp(ctx, sh.count);
+    // chunks of the generic path would share the Fenwick columns: one chunk
+    res->chunks = pl.generic ? std::vector<Shard>{{0, sh.count}} : make_chunks(sh.count, +1);
     const size_t nc = res->chunks.size();
     res->chunk_base.assign(nc, 0); res->chunk_total.assign(nc, 0);
     res->local_off.assign(sh.count + 1, 0);
@@ -802,7 +885,7 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
         uint64_t w = 0;
         for (uint64_t i = 0; i < res->chunks[k].count; ++i) {
             const uint64_t b = res->chunks[k].first + i;
-            w += redux_compress_bound(rel[b + 1] - rel[b], pl.c);
+            w += redux_compress_bound_ex(rel[b + 1] - rel[b], pl.s, pl.c);
         }
         chunk_cap[k] = w;
         res->chunk_base[k] = dcap;
@@ -820,6 +903,7 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     CU_TRY(ctx, d->pin_status.reserve(sh.count * sizeof(int32_t)));
     const void *magic = nullptr;
     if ((rc = get_magic(ctx, d, d->h2d, pl, &magic))) return rc;
+    if ((rc = prepare_generic(ctx, d, d->h2d, p, sh.count, &pl))) return rc;
     EventSet evs;                       // [0, nc): chunk done; [nc, 2nc): chunk input on the device
     CU_TRY(ctx, evs.create(2 * nc));
     CU_TRY(ctx, cudaMemcpyAsync(d->st_off.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d->h2d));
@@ -970,8 +1054,8 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     Plan pl;
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
-    pl.warp = choose_warp(ctx, sh.count);
-    const std::vector<Shard> chunks = make_chunks(sh.count, -1);
+    pl.warp = !pl.generic && choose_warp(ctx, sh.count);
+    const std::vector<Shard> chunks = pl.generic ? std::vector<Shard>{{0, sh.count}} : make_chunks(sh.count, -1);
     const size_t nc = chunks.size();
     CU_TRY(ctx, d->st_in.reserve(cbytes + 32));
     CU_TRY(ctx, d->st_off.reserve(rel.size() * sizeof(uint64_t)));
@@ -984,6 +1068,7 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     CU_TRY(ctx, d->pin_status.reserve(sh.count * sizeof(int32_t)));
     const void *magic = nullptr;
     if ((rc = get_magic(ctx, d, d->pipe[0], pl, &magic))) return rc;
+    if ((rc = prepare_generic(ctx, d, d->pipe[0], p, sh.count, &pl))) return rc;
     EventSet evs;                       // chunk input on the device
     CU_TRY(ctx, evs.create(nc));
     CU_TRY(ctx, cudaMemcpyAsync(d->st_off.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d->h2d));
@@ -1088,5 +1173,33 @@ extern "C" int redux_decompress(redux_ctx_t *ctx, int model_kind, const redux_pa
         if (in_count) *in_count = consumed;
         if (out_count) *out_count = raw_len;
     }
+    return rc;
+}
+
+// ================================================================== pre-trained models (8(f) rank 4)
+
+extern "C" int redux_encode_batch_ex(redux_ctx_t *ctx, int model_kind, const redux_params_t *params,
+                                     const uint32_t *model_freq, const uint8_t *in, const uint64_t *in_offsets,
+                                     uint64_t n_blocks, uint8_t *out, uint64_t out_capacity,
+                                     uint64_t *out_offsets, int32_t *status)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    ctx->model_freq = model_freq;
+    const int rc = redux_encode_batch(ctx, model_kind, params, in, in_offsets, n_blocks, out, out_capacity,
+                                      out_offsets, status);
+    ctx->model_freq = nullptr;
+    return rc;
+}
+
+extern "C" int redux_decode_batch_ex(redux_ctx_t *ctx, int model_kind, const redux_params_t *params,
+                                     const uint32_t *model_freq, const uint8_t *comp, const uint64_t *comp_offsets,
+                                     uint64_t n_blocks, uint8_t *raw, const uint64_t *raw_offsets,
+                                     uint64_t *raw_lens, uint64_t *consumed, int32_t *status)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    ctx->model_freq = model_freq;
+    const int rc = redux_decode_batch(ctx, model_kind, params, comp, comp_offsets, n_blocks, raw, raw_offsets,
+                                      raw_lens, consumed, status);
+    ctx->model_freq = nullptr;
     return rc;
 }

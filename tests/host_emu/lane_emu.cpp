@@ -9,6 +9,7 @@ thread_local EmuIdx threadIdx, blockIdx, blockDim, gridDim;
 
 #include "../../redux_b200/csrc/redux_lane_codec.cuh"
 #include "../../redux_b200/csrc/redux_lane_al.cuh"
+#include "../../redux_b200/csrc/redux_generic_codec.cuh"
 
 namespace rdx {
 // dynamic shared memory of one CTA: 7 warps x 256 nodes x 32 lanes x 4 B
@@ -144,4 +145,58 @@ extern "C" uint32_t emu_step_al(uint32_t c, uint32_t f, uint32_t low, uint32_t h
     v = (v << sink.nb) | (sink.acc & ((sink.nb ? (1ull << sink.nb) : 1ull) - 1));
     *bits = v; *nbits = sink.wi * 32 + sink.nb; *pend_after = pend;
     return n;
+}
+
+// ------------------------------------------------------------------ generic path (any symbol width, pre-trained models)
+namespace {
+struct GenericSetup { std::vector<uint32_t> init, tabs; GenericJob job; };
+
+void generic_setup(GenericSetup &g, uint32_t s, uint32_t f, uint32_t c, const uint32_t *freq, uint32_t n_threads)
+{
+    const uint32_t nsym = (1u << s) + 1;
+    g.init.assign(nsym + 1, 0);
+    blockDim.x = 256; gridDim.x = (nsym + 1 + 255) / 256;
+    for (uint32_t b = 0; b < gridDim.x; ++b)
+        for (uint32_t t = 0; t < 256; ++t) { blockIdx.x = b; threadIdx.x = t; build_tree_kernel(freq, nsym, g.init.data()); }
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nsym; ++i) total += freq ? freq[i] : 1u;
+    g.tabs.assign((size_t)(nsym + 1) * n_threads, 0xDEADBEEFu);
+    g.job = GenericJob{};
+    g.job.tabs = g.tabs.data(); g.job.init_tree = g.init.data(); g.job.init_total = (uint32_t)total;
+    g.job.s = s; g.job.f = f; g.job.c = c; g.job.n_threads = n_threads;
+}
+
+template <typename K>
+void run_generic(K kernel, const GenericJob &job)
+{
+    blockDim.x = kGenericThreads; gridDim.x = job.n_threads / kGenericThreads;
+    for (uint32_t b = 0; b < gridDim.x; ++b)
+        for (uint32_t t = 0; t < (uint32_t)kGenericThreads; ++t) { blockIdx.x = b; threadIdx.x = t; kernel(job); }
+}
+}  // namespace
+
+// n_threads: multiple of 128; fewer threads than blocks makes threads code several blocks in turn
+extern "C" int emu_encode_generic(uint32_t s, uint32_t f, uint32_t c, const uint32_t *freq, uint32_t n_threads,
+                                  const uint8_t *in, const uint64_t *in_off, uint64_t n_blocks,
+                                  uint8_t *slots, uint64_t slot_stride, uint32_t *sizes, int32_t *status)
+{
+    GenericSetup g;
+    generic_setup(g, s, f, c, freq, n_threads);
+    g.job.in = in; g.job.in_off = in_off; g.job.n_blocks = n_blocks;
+    g.job.slots = slots; g.job.slot_stride = slot_stride; g.job.sizes = sizes; g.job.status = status;
+    run_generic(encode_generic_kernel, g.job);
+    return 0;
+}
+
+extern "C" int emu_decode_generic(uint32_t s, uint32_t f, uint32_t c, const uint32_t *freq, uint32_t n_threads,
+                                  const uint8_t *comp, const uint64_t *comp_off, uint64_t n_blocks,
+                                  uint8_t *raw, const uint64_t *raw_off, uint64_t *raw_len, uint64_t *consumed,
+                                  int32_t *status)
+{
+    GenericSetup g;
+    generic_setup(g, s, f, c, freq, n_threads);
+    g.job.in = comp; g.job.in_off = comp_off; g.job.n_blocks = n_blocks;
+    g.job.raw = raw; g.job.raw_off = raw_off; g.job.raw_len = raw_len; g.job.consumed = consumed; g.job.status = status;
+    run_generic(decode_generic_kernel, g.job);
+    return 0;
 }

@@ -68,6 +68,10 @@ def lib():
         fn = getattr(L, name)
         fn.argtypes = [C.c_int, u64, u64, u64, p8, C.c_size_t, p8, C.c_size_t, pu64, pu64]
         fn.restype = C.c_int
+    for name in ("oracle_compress_trained", "oracle_decompress_trained"):
+        fn = getattr(L, name)
+        fn.argtypes = [C.c_int, u64, u64, u64, p8, C.c_size_t, p8, C.c_size_t, p8, C.c_size_t, pu64, pu64]
+        fn.restype = C.c_int
     L.oracle_compress_bound.argtypes = [C.c_size_t, u64, u64]
     L.oracle_compress_bound.restype = C.c_size_t
     L.oracle_compress_batch.argtypes = [C.c_int, u64, u64, u64, p8, p8, u64, p8, p8, p8, p8, C.c_int]
@@ -115,6 +119,38 @@ def decompress(data, kind=TREE, params=(8, 30, 32), out_cap=None):
     rc = lib().oracle_decompress(kind, s, f, c, a.ctypes.data, a.size, out.ctypes.data, cap,
                                  C.byref(ic), C.byref(oc))
     return rc, out[:oc.value].tobytes(), ic.value, oc.value
+
+
+def _trained(fn, data, train, kind, params, cap):
+    a = _as_u8(data)
+    tr = np.ascontiguousarray(train, dtype=np.uint64)
+    s, f, c = params
+    out = np.zeros(cap, dtype=np.uint8)
+    ic, oc = C.c_uint64(0), C.c_uint64(0)
+    rc = fn(kind, s, f, c, tr.ctypes.data, tr.size, a.ctypes.data, a.size, out.ctypes.data, cap, C.byref(ic), C.byref(oc))
+    return rc, out[:oc.value].tobytes(), ic.value, oc.value
+
+
+def compress_trained(data, train, kind=TREE, params=(8, 30, 32), out_cap=None):
+    """compress() with a model the caller trained by calling get_frequency(sym) for sym in `train` first."""
+    s, f, c = params
+    cap = out_cap if out_cap is not None else max(16, (len(data) * 8 // s + 1) * 8 + 16)
+    return _trained(lib().oracle_compress_trained, data, train, kind, params, cap)
+
+
+def decompress_trained(data, train, kind=TREE, params=(8, 30, 32), out_cap=None):
+    cap = out_cap if out_cap is not None else max(64, len(data) * 64 + 1024)
+    return _trained(lib().oracle_decompress_trained, data, train, kind, params, cap)
+
+
+def trained_frequencies(train, kind=TREE, params=(8, 30, 32)):
+    """Per-symbol frequency vector of a model after get_frequency(sym) for sym in `train` (uint32[symbol_count])."""
+    m = Model(kind, *params)
+    for t in train:
+        rc, lo, hi = m.get_frequency(int(t))
+        assert rc == OK
+    tab = m.get_freq_table()
+    return (tab[:, 1] - tab[:, 0]).astype(np.uint32)
 
 
 def compress_batch(inp, in_off, kind=TREE, params=(8, 30, 32), threads=1):

@@ -20,9 +20,9 @@ int main(void) {
         p.code_half != (2ull << 30) || p.code_max != 0xFFFFFFFFull) return 2;
     if (redux_parameters_new(8, 9, 16, NULL) != REDUX_INVALID_INPUT) return 3;     /* src/model/mod.rs:64 */
     if (redux_parameters_new(8, 40, 42, NULL) != REDUX_INVALID_INPUT) return 4;    /* code + freq > 64 */
-    redux_params_t q = {4, 10, 16};
-    if (redux_params_supported(&q) != REDUX_UNSUPPORTED) return 5;
-    if (redux_compress_bound(0, 16) != 2) return 6;
+    redux_params_t q = {4, 10, 16}, q17 = {17, 20, 24};
+    if (redux_params_supported(&q) != REDUX_OK || redux_params_supported(&q17) != REDUX_UNSUPPORTED) return 5;
+    if (redux_compress_bound(0, 16) != 2 || redux_compress_bound_ex(7, 12, 16) != 10) return 6;
     if (strcmp(redux_error_string(REDUX_EOF), "Unexpected end of file") != 0) return 7;
     uint64_t first, count;
     redux_debug_shard(65536, 8, 3, &first, &count);

@@ -53,8 +53,10 @@ def test_params_supported_scope():
     mk = lambda s, f, c: C.byref(rb._ParamsC(s, f, c))
     assert L.redux_params_supported(mk(8, 14, 16)) == rb.OK
     assert L.redux_params_supported(mk(8, 30, 34)) == rb.OK
-    assert L.redux_params_supported(mk(4, 10, 16)) == rb.UNSUPPORTED
-    assert L.redux_params_supported(mk(12, 14, 16)) == rb.UNSUPPORTED
+    assert L.redux_params_supported(mk(4, 10, 16)) == rb.OK          # generic path: any width up to 16
+    assert L.redux_params_supported(mk(12, 14, 16)) == rb.OK
+    assert L.redux_params_supported(mk(16, 18, 20)) == rb.OK
+    assert L.redux_params_supported(mk(17, 19, 21)) == rb.UNSUPPORTED
     assert L.redux_params_supported(mk(8, 9, 16)) == rb.INVALID_INPUT
 
 

@@ -243,9 +243,13 @@ def test_invalid_and_unsupported_parameters(ctx):
     with pytest.raises(rb.InvalidInput):
         rb.Parameters(8, 9, 16)
     data, off = concat([b"abc"])
-    model = rb.AdaptiveTreeModel(rb.Parameters(4, 10, 16))
+    model = rb.AdaptiveTreeModel(rb.Parameters(17, 20, 24))      # valid Parameters beyond the device scope
     with pytest.raises(rb.Unsupported):
         ctx.encode_batch(data, off, model)
+    trained = rb.AdaptiveTreeModel(rb.Parameters(8, 10, 12))
+    trained.freq = np.full(257, 4, dtype=np.uint32)              # total 1028 > freq_max 1023
+    with pytest.raises(rb.InvalidInput):
+        ctx.encode_batch(data, off, trained)
 
 
 def test_generator_device_equals_host(ctx):
@@ -296,3 +300,90 @@ def test_device_resident_batch_roundtrip_and_sampled_parity(ctx):
     assert bool((raw_lens == L).all())
     assert bool((consumed == (comp_off[1:] - comp_off[:-1])).all())
     assert torch.equal(back, raw)
+
+
+# ------------------------------------------------------------------ SURVEY 8(f) rank 4
+GENERIC_PARAMS = [(4, 10, 16), (4, 14, 16), (4, 30, 32), (12, 14, 16), (12, 22, 24), (12, 30, 32),
+                  (1, 3, 5), (5, 8, 11), (7, 20, 40), (16, 18, 20)]
+
+
+@pytest.mark.parametrize("params", GENERIC_PARAMS)
+def test_generic_symbol_widths(ctx, params):
+    """symbol_bits != 8 (the widths of src/model/tests.rs:95-251 and some odd ones): compressed bytes equal
+    compress(); decoding equals decompress() including the reference's quirks when 8 % symbol_bits != 0
+    (trailing partial symbol dropped on encode, no final flush on decode)."""
+    rng = np.random.default_rng(sum(params))
+    blocks = [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in (0, 1, 2, 3, 7, 64, 333, 1000)]
+    blocks += [bytes(rng.choice(np.frombuffer(b"abcd \n", dtype=np.uint8), 500)), bytes([0xFF] * 257)]
+    for cls, okind in KINDS:
+        model = cls(rb.Parameters(*params))
+        data, off = concat(blocks)
+        out, out_off, status = ctx.encode_batch(data, off, model)
+        assert (status == 0).all()
+        want, back = [], []
+        for i, b in enumerate(blocks):
+            rc, e, ic, oc = o.compress(b, okind, params)
+            assert rc == o.OK
+            assert out[int(out_off[i]):int(out_off[i + 1])].tobytes() == e, (params, i)
+            rc, d, ic2, oc2 = o.decompress(e, okind, params, out_cap=len(b) + 8)
+            assert rc == o.OK
+            back.append(d)
+        raw_off = np.zeros(len(blocks) + 1, dtype=np.uint64)
+        np.cumsum(np.array([len(b) + 8 for b in blocks], dtype=np.uint64), out=raw_off[1:])
+        raw, raw_lens, consumed, status = ctx.decode_batch(out, out_off, raw_off, model)
+        assert (status == 0).all()
+        for i, d in enumerate(back):
+            assert raw[int(raw_off[i]):int(raw_off[i]) + int(raw_lens[i])].tobytes() == d, (params, i)
+            assert int(consumed[i]) == int(out_off[i + 1] - out_off[i])
+
+
+@pytest.mark.parametrize("params", [(8, 14, 16), (8, 30, 32), (4, 10, 16), (12, 22, 24)])
+def test_pretrained_models(ctx, params):
+    """A model trained through get_frequency() before compress()/decompress() receive it (the reference's
+    Box<Model> may arrive in any state, src/lib.rs:102 + src/model/mod.rs:23-25)."""
+    s, f, c = params
+    rng = np.random.default_rng(77 + s)
+    train = [int(x) for x in rng.integers(0, min((1 << s) + 1, 40), 1500)]
+    blocks = [bytes(rng.integers(0, 40, n, dtype=np.uint8)) for n in (0, 1, 5, 100, 2000)]
+    for cls, okind in KINDS:
+        model = cls(rb.Parameters(*params)).train(train)
+        assert (model.freq == o.trained_frequencies(train, okind, params)).all()
+        assert model.total_frequency() == min((1 << s) + 1 + len(train), (1 << f) - 1)
+        single = cls(rb.Parameters(*params))
+        for t in train[:20]:
+            single.get_frequency(t)                              # the reference's own training call
+        assert (single.freq == o.trained_frequencies(train[:20], okind, params)).all()
+        data, off = concat(blocks)
+        out, out_off, status = ctx.encode_batch(data, off, model)
+        assert (status == 0).all()
+        raw_off = np.zeros(len(blocks) + 1, dtype=np.uint64)
+        np.cumsum(np.array([len(b) + 4 for b in blocks], dtype=np.uint64), out=raw_off[1:])
+        raw, raw_lens, consumed, status = ctx.decode_batch(out, out_off, raw_off, model)
+        assert (status == 0).all()
+        for i, b in enumerate(blocks):
+            rc, e, ic, oc = o.compress_trained(b, train, okind, params)
+            assert rc == o.OK and out[int(out_off[i]):int(out_off[i + 1])].tobytes() == e, (params, i)
+            rc, d, ic2, oc2 = o.decompress_trained(e, train, okind, params, out_cap=len(b) + 4)
+            assert raw[int(raw_off[i]):int(raw_off[i]) + int(raw_lens[i])].tobytes() == d
+        # the drop-in pair with a trained model
+        cbuf = io.BytesIO()
+        counts = rb.compress(io.BytesIO(blocks[3]), cbuf, cls(rb.Parameters(*params)).train(train), context=ctx)
+        assert cbuf.getvalue() == o.compress_trained(blocks[3], train, okind, params)[1] and counts[0] == len(blocks[3])
+        dbuf = io.BytesIO()
+        rb.decompress(io.BytesIO(cbuf.getvalue()), dbuf, cls(rb.Parameters(*params)).train(train), context=ctx)
+        assert dbuf.getvalue() == o.decompress_trained(cbuf.getvalue(), train, okind, params)[1]
+
+
+def test_generic_many_blocks_share_columns(ctx):
+    """More blocks than the generic kernel has threads per launch slot reuse: 5,000 blocks of 12-bit symbols."""
+    params = (12, 14, 16)
+    n, L = 5000, 96
+    raw = rb.generate_blocks_host(0, n, L, SEED)
+    off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+    model = rb.AdaptiveTreeModel(rb.Parameters(*params))
+    out, out_off, status = ctx.encode_batch(raw, off, model)
+    assert (status == 0).all()
+    for i in (0, 1, 127, 128, 4095, 4999):
+        assert out[int(out_off[i]):int(out_off[i + 1])].tobytes() == o.compress(raw[i * L:(i + 1) * L], o.TREE, params)[1]
+    back, lens, cons, status = ctx.decode_batch(out, out_off, off, model)
+    assert (status == 0).all() and (back[: n * L] == raw).all()      # 96 bytes = 64 whole 12-bit symbols

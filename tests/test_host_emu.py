@@ -25,7 +25,7 @@ SEED = 0x5EED202610180000
 def _build():
     srcs = [os.path.join(EMU_DIR, "lane_emu.cpp"), os.path.join(EMU_DIR, "cuda_shim.h"),
             os.path.join(CSRC, "redux_lane_codec.cuh"), os.path.join(CSRC, "redux_lane_al.cuh"),
-            os.path.join(CSRC, "redux_common.cuh")]
+            os.path.join(CSRC, "redux_generic_codec.cuh"), os.path.join(CSRC, "redux_common.cuh")]
     if os.path.exists(EMU_SO) and all(os.path.getmtime(s) <= os.path.getmtime(EMU_SO) for s in srcs):
         return
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
@@ -41,6 +41,8 @@ def emu():
     L.emu_slot_stride.restype = u64
     L.emu_encode_lane.argtypes = [u32, u32, u64, i32, vp, vp, u64, vp, vp, vp]
     L.emu_decode_lane.argtypes = [u32, u32, u64, i32, vp, vp, u64, vp, vp, vp, vp, vp]
+    L.emu_encode_generic.argtypes = [u32, u32, u32, vp, u32, vp, vp, u64, vp, u64, vp, vp]
+    L.emu_decode_generic.argtypes = [u32, u32, u32, vp, u32, vp, vp, u64, vp, vp, vp, vp, vp]
     return L
 
 
@@ -242,3 +244,126 @@ def test_al_step_closed_form_equals_loop(emu):
             assert got == want, (c, f, low, high, cl, ch, count, got, want)
             collapsed += want[2] == c
         assert collapsed > 0 or f + 2 < c, "no collapsed interval exercised for (f,c)=(%d,%d)" % (f, c)
+
+
+# ------------------------------------------------------------------ generic path
+def gen_encode(emu, blocks, params, freq=None, n_threads=128):
+    s, f, c = params
+    data, off = concat(blocks)
+    n = len(blocks)
+    max_len = max((len(b) for b in blocks), default=0)
+    bound = ((max_len * 8 // s + 1) * c + 7) // 8
+    stride = ((bound + 15) & ~15) + 16
+    slots = np.zeros(n * stride + 64, dtype=np.uint8)
+    base = (-slots.ctypes.data) % 16
+    sizes = np.zeros(n, dtype=np.uint32)
+    status = np.full(n, -1, dtype=np.int32)
+    fq = None if freq is None else np.ascontiguousarray(freq, dtype=np.uint32)
+    emu.emu_encode_generic(s, f, c, None if fq is None else fq.ctypes.data, n_threads, data.ctypes.data,
+                           off.ctypes.data, n, slots.ctypes.data + base, stride, sizes.ctypes.data, status.ctypes.data)
+    assert (status == 0).all()
+    return [slots[base + i * stride: base + i * stride + int(sizes[i])].tobytes() for i in range(n)]
+
+
+def gen_decode(emu, streams, caps, params, freq=None, n_threads=128):
+    s, f, c = params
+    comp, coff = concat(streams)
+    n = len(streams)
+    roff = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(np.array(caps, dtype=np.uint64), out=roff[1:])
+    raw = np.zeros(int(roff[-1]) + 64, dtype=np.uint8)
+    raw_len = np.zeros(n, dtype=np.uint64)
+    consumed = np.zeros(n, dtype=np.uint64)
+    status = np.full(n, -1, dtype=np.int32)
+    fq = None if freq is None else np.ascontiguousarray(freq, dtype=np.uint32)
+    emu.emu_decode_generic(s, f, c, None if fq is None else fq.ctypes.data, n_threads, comp.ctypes.data,
+                           coff.ctypes.data, n, raw.ctypes.data, roff.ctypes.data, raw_len.ctypes.data,
+                           consumed.ctypes.data, status.ctypes.data)
+    return [raw[int(roff[i]): int(roff[i]) + int(raw_len[i])].tobytes() for i in range(n)], raw_len, consumed, status
+
+
+# the widths and (freq, code) pairs of the reference's model tests (src/model/tests.rs:95-251) + odd ones
+GENERIC_PARAMS = [(4, 10, 16), (4, 14, 16), (4, 30, 32), (12, 14, 16), (12, 22, 24), (12, 30, 32),
+                  (1, 3, 5), (3, 5, 7), (5, 8, 11), (7, 20, 40), (8, 14, 16), (16, 18, 20), (11, 31, 33)]
+
+
+@pytest.mark.parametrize("params", GENERIC_PARAMS)
+def test_generic_kernels_equal_oracle(emu, params):
+    """Any symbol width: bytes equal compress(), decode equals decompress() -- including the reference's
+    quirks for widths that do not divide 8 (trailing partial symbol dropped; decoder never flushes)."""
+    rng = np.random.default_rng(sum(params))
+    blocks = make_blocks(rng, 30, 600 if params[0] < 12 else 1500)
+    blocks += [bytes(rng.integers(0, 256, 777, dtype=np.uint8)), bytes([0xFF] * 301)]
+    want, back = [], []
+    for b in blocks:
+        rc, out, ic, oc = o.compress(b, o.TREE, params)
+        assert rc == o.OK and ic == len(b)
+        want.append(out)
+        rc, dec, ic2, oc2 = o.decompress(out, o.LINEAR, params, out_cap=len(b) + 8)
+        assert rc == o.OK and ic2 == len(out)
+        back.append(dec)
+    got = gen_encode(emu, blocks, params, n_threads=128)     # 32 blocks on 128 threads ...
+    assert got == want
+    got = gen_encode(emu, blocks[:20], params, n_threads=128)
+    assert got == want[:20]
+    outs, raw_len, consumed, status = gen_decode(emu, want, [len(b) + 8 for b in blocks], params)
+    assert (status == 0).all()
+    assert outs == back                                       # what decompress() writes (may lose trailing bits)
+    assert [int(x) for x in consumed] == [len(w) for w in want]
+    if 8 % params[0] == 0:
+        assert back == blocks
+
+
+def test_generic_threads_reuse_columns(emu):
+    """More blocks than threads: a thread codes several blocks in turn and must reset its column."""
+    rng = np.random.default_rng(3)
+    params = (8, 14, 16)
+    blocks = make_blocks(rng, 300, 300)
+    want = [o.compress(b, o.TREE, params)[1] for b in blocks]
+    assert gen_encode(emu, blocks, params, n_threads=128) == want
+    outs, raw_len, consumed, status = gen_decode(emu, want, [len(b) for b in blocks], params, n_threads=128)
+    assert (status == 0).all() and outs == blocks
+
+
+@pytest.mark.parametrize("params", [(8, 14, 16), (8, 30, 32), (4, 10, 16), (12, 22, 24)])
+def test_pretrained_models_equal_oracle(emu, params):
+    """A model trained before compress()/decompress() got it (Model::get_frequency mutates,
+    src/model/mod.rs:23-25): the device path starts every block from that frequency vector."""
+    s, f, c = params
+    rng = np.random.default_rng(s * 100 + f)
+    nsym = (1 << s) + 1
+    for n_train in (1, 50, 3000):
+        train = rng.integers(0, min(nsym, 40), n_train)      # skewed; includes possibly freezing the model (f=10)
+        freq = o.trained_frequencies(train, o.TREE, params)
+        assert freq.sum() == min(nsym + n_train, (1 << f) - 1)
+        blocks = make_blocks(rng, 12, 400)
+        want = []
+        for b in blocks:
+            rc, out, ic, oc = o.compress_trained(b, train, o.LINEAR, params)
+            assert rc == o.OK
+            want.append(out)
+        assert gen_encode(emu, blocks, params, freq=freq) == want
+        outs, raw_len, consumed, status = gen_decode(emu, want, [len(b) + 4 for b in blocks], params, freq=freq)
+        assert (status == 0).all()
+        for i, w in enumerate(want):
+            rc, dec, ic, oc = o.decompress_trained(w, train, o.TREE, params, out_cap=len(blocks[i]) + 4)
+            assert rc == o.OK and outs[i] == dec and int(consumed[i]) == ic
+
+
+def test_generic_truncated_and_full(emu):
+    params = (12, 14, 16)
+    rng = np.random.default_rng(9)
+    blocks = [bytes(rng.integers(0, 256, n, dtype=np.uint8)) for n in (30, 31, 32, 33, 100, 3)]
+    streams = [o.compress(b, o.TREE, params)[1] for b in blocks]
+    cut = [s[:-1 - (i % 3)] for i, s in enumerate(streams)] + [b"", b"\x00"]
+    caps = [len(b) + 8 for b in blocks] + [4, 4]
+    outs, raw_len, consumed, status = gen_decode(emu, cut, caps, params)
+    for i, s in enumerate(cut):
+        rc, out, ic, oc = o.decompress(s, o.TREE, params, out_cap=caps[i])
+        assert (int(status[i]), outs[i], int(consumed[i])) == (rc, out, ic), i
+    # a slot one byte too small: the reference's writer fails (IoError) -> OUT_CAPACITY here, prefix in place
+    outs, raw_len, consumed, status = gen_decode(emu, streams, [max(0, (len(b) * 8 // 12 * 12) // 8 - 1) for b in blocks], params)
+    for i, s in enumerate(streams):
+        cap = max(0, (len(blocks[i]) * 8 // 12 * 12) // 8 - 1)
+        rc, out, ic, oc = o.decompress(s, o.TREE, params, out_cap=cap)
+        assert rc == o.IO_ERROR and int(status[i]) == 6 and outs[i] == out, (i, rc, int(status[i]))
