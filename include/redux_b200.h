@@ -38,6 +38,8 @@ extern "C" {
 #define REDUX_SCHED_AUTO 0      /* choose by batch shape */
 #define REDUX_SCHED_LANE 1      /* one stream per lane, 32 streams per warp: throughput mapping */
 #define REDUX_SCHED_WARP 2      /* one stream per warp, lanes cooperate per symbol: latency mapping */
+#define REDUX_SCHED_SPLIT 3     /* encode: model phase parallel over the positions of a stream, then one coder warp
+                                   per stream (few long streams); decode: as REDUX_SCHED_WARP */
 
 /* Parameters::new arguments (src/model/mod.rs:63). */
 typedef struct redux_params {

@@ -27,7 +27,7 @@ _SO = os.path.join(_HERE, "libredux_b200.so")
 
 OK, EOF, INVALID_INPUT, IO_ERROR, CUDA_ERROR, UNSUPPORTED, OUT_CAPACITY = range(7)
 MODEL_LINEAR, MODEL_TREE = 0, 1
-SCHED_AUTO, SCHED_LANE, SCHED_WARP = 0, 1, 2
+SCHED_AUTO, SCHED_LANE, SCHED_WARP, SCHED_SPLIT = 0, 1, 2, 3
 
 
 # --------------------------------------------------------------------------- errors (src/lib.rs:57-84)

@@ -22,6 +22,7 @@
 #include "redux_lane_al.cuh"
 #include "redux_generic_codec.cuh"
 #include "redux_warp_codec.cuh"
+#include "redux_split_encoder.cuh"
 
 using namespace rdx;
 
@@ -79,6 +80,7 @@ struct DeviceState {
     HostBuf pin_off, pin_status, pin_aux0, pin_aux1;
     DevBuf slots, sizes, flag;                 // encoder workspace
     DevBuf st_in, st_off, st_out, st_ooff, st_status, st_aux0, st_aux1, st_roff;   // host-API staging
+    DevBuf split_hist, split_pairs;            // split encoder: chunk histograms, per-position ranges
     DevBuf gen_tabs, gen_init, gen_freq;       // generic path: Fenwick columns, start tree, uploaded frequencies
     uint8_t *text_lut = nullptr;
     std::vector<MagicEntry> magics;
@@ -159,6 +161,8 @@ struct Plan {
     bool generic = false; uint32_t s = 8, gen_threads = 0, gen_total = 0;
     uint32_t *gen_tabs = nullptr; const uint32_t *gen_init = nullptr;
     bool warp = false;      // one stream per warp (latency mapping) instead of one per lane
+    bool split = false;     // encode only: parallel model phase + one-warp coder chain (redux_split_encoder.cuh)
+    uint64_t max_len = 0;   // longest block of the launch
 };
 
 // REDUX_SCHED_AUTO: with this few streams both mappings are bound by the serial latency of the longest
@@ -169,9 +173,20 @@ constexpr uint64_t kWarpAutoMaxBlocks = 512;
 
 bool choose_warp(const redux_ctx *ctx, uint64_t n_blocks)
 {
-    if (ctx->sched == REDUX_SCHED_WARP) return true;
+    if (ctx->sched == REDUX_SCHED_WARP || ctx->sched == REDUX_SCHED_SPLIT) return true;
     if (ctx->sched == REDUX_SCHED_LANE) return false;
     return n_blocks < kWarpAutoMaxBlocks;
+}
+
+// The split encoder needs 8 bytes of workspace per input position; beyond 2 GB the warp mapping is used.
+constexpr uint64_t kSplitMaxPairBytes = (uint64_t)2 << 30;
+bool choose_split(const redux_ctx *ctx, uint64_t n_blocks, int cls, uint64_t max_len)
+{
+    if (ctx->sched == REDUX_SCHED_LANE || ctx->sched == REDUX_SCHED_WARP) return false;
+    if (ctx->sched == REDUX_SCHED_AUTO && n_blocks >= kWarpAutoMaxBlocks) return false;
+    if (cls == kHuge || max_len == 0) return false;
+    const uint64_t stride = (max_len + 31) & ~(uint64_t)31;
+    return n_blocks * stride * sizeof(uint2) <= kSplitMaxPairBytes;
 }
 
 int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, Plan *pl)
@@ -184,6 +199,7 @@ int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, P
     if (max_block_len > 0xFFFFFFF0ull)
         return fail(ctx, REDUX_UNSUPPORTED, "blocks longer than 2^32-16 bytes are not supported");
     pl->s = p->symbol_bits;
+    pl->max_len = max_block_len;
     pl->generic = p->symbol_bits != (uint32_t)kSymbolBits || ctx->model_freq != nullptr;
     if (pl->generic) {
         // worst case: every coded symbol (floor(8 len / s) data symbols + EOF) emits code_bits bits
@@ -322,6 +338,30 @@ void launch_decode_warp(int cls, const LaneDecJob &job, cudaStream_t s)
     if (cls == kNarrow)    decode_warp_kernel<kNarrow><<<grid, kWarpCtaThreads, 0, s>>>(job);
     else if (cls == kWide) decode_warp_kernel<kWide><<<grid, kWarpCtaThreads, 0, s>>>(job);
     else                   decode_warp_kernel<kHuge><<<grid, kWarpCtaThreads, 0, s>>>(job);
+}
+
+// Split encoder: model phase over all chunks of all streams, then one coder warp per stream.
+int launch_encode_split(redux_ctx *ctx, DeviceState *d, const Plan &pl, const LaneEncJob &job, cudaStream_t s)
+{
+    if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
+    SplitJob sj;
+    sj.in = job.in; sj.in_off = job.in_off; sj.n_blocks = job.n_blocks;
+    sj.chunks_per_stream = (uint32_t)((pl.max_len + kSplitChunk - 1) / kSplitChunk);
+    sj.pair_stride = (pl.max_len + 31) & ~(uint64_t)31;
+    sj.tcap = pl.tcap;
+    const uint64_t chunks = job.n_blocks * sj.chunks_per_stream;
+    CU_TRY(ctx, d->split_hist.reserve(chunks * 256 * sizeof(uint32_t)));
+    CU_TRY(ctx, d->split_pairs.reserve(job.n_blocks * sj.pair_stride * sizeof(uint2)));
+    sj.hist = (uint32_t *)d->split_hist.p; sj.pairs = (uint2 *)d->split_pairs.p;
+    split_hist_kernel<<<(uint32_t)chunks, 256, 0, s>>>(sj);
+    split_scan_kernel<<<(uint32_t)job.n_blocks, 256, 0, s>>>(sj);
+    split_model_kernel<<<(uint32_t)((chunks + kSplitModelWarps - 1) / kSplitModelWarps), kSplitModelWarps * 32, 0, s>>>(sj);
+    const uint32_t grid = (uint32_t)job.n_blocks;
+    if (pl.cls == kNarrow)   split_coder_kernel<kNarrow, false><<<grid, 32, 0, s>>>(job, sj);
+    else if (pl.c == 32)     split_coder_kernel<kWide, true><<<grid, 32, 0, s>>>(job, sj);
+    else                     split_coder_kernel<kWide, false><<<grid, 32, 0, s>>>(job, sj);
+    ctx->launches += 3;      // + the one counted by the caller
+    return REDUX_OK;
 }
 
 int check_kind(redux_ctx *ctx, int kind)
@@ -504,7 +544,7 @@ extern "C" void redux_ctx_destroy(redux_ctx_t *ctx)
         for (int i = 0; i < kPipeStreams; ++i) if (d.pipe[i]) cudaStreamDestroy(d.pipe[i]);
         for (HostBuf *b : {&d.pin_off, &d.pin_status, &d.pin_aux0, &d.pin_aux1}) b->release();
         for (DevBuf *b : {&d.slots, &d.sizes, &d.flag, &d.st_in, &d.st_off, &d.st_out, &d.st_ooff,
-                          &d.st_status, &d.st_aux0, &d.st_aux1, &d.st_roff, &d.gen_tabs, &d.gen_init, &d.gen_freq}) b->release();
+                          &d.st_status, &d.st_aux0, &d.st_aux1, &d.st_roff, &d.gen_tabs, &d.gen_init, &d.gen_freq, &d.split_hist, &d.split_pairs}) b->release();
         for (auto &m : d.magics) cudaFree(m.ptr);
         if (d.text_lut) cudaFree(d.text_lut);
     }
@@ -542,7 +582,7 @@ extern "C" int redux_ctx_timing_collect(redux_ctx_t *ctx, double *ms, uint64_t *
 extern "C" int redux_ctx_set_schedule(redux_ctx_t *ctx, int sched)
 {
     if (!ctx) return REDUX_INVALID_INPUT;
-    if (sched == REDUX_SCHED_AUTO || sched == REDUX_SCHED_LANE || sched == REDUX_SCHED_WARP) { ctx->sched = sched; return REDUX_OK; }
+    if (sched == REDUX_SCHED_AUTO || sched == REDUX_SCHED_LANE || sched == REDUX_SCHED_WARP || sched == REDUX_SCHED_SPLIT) { ctx->sched = sched; return REDUX_OK; }
     return fail(ctx, REDUX_INVALID_INPUT, "unknown schedule");
 }
 
@@ -581,6 +621,11 @@ int encode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
             g.in = d_in; g.in_off = d_in_off; g.n_blocks = n_blocks;
             g.slots = slots; g.slot_stride = pl.slot_stride; g.sizes = sizes; g.status = d_status;
             encode_generic_kernel<<<pl.gen_threads / kGenericThreads, kGenericThreads, 0, s>>>(g);
+        }
+        else if (pl.split) {
+            DeviceState *d = find_dev(ctx, device);
+            int rc = launch_encode_split(ctx, d, pl, job, s);
+            if (rc) return rc;
         }
         else if (pl.warp)       launch_encode_warp(pl.cls, job, s);
         else if (pl.aligned)    launch_encode_al(pl, job, grid, smem, s);
@@ -650,6 +695,7 @@ extern "C" int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *str
     Plan pl;
     if ((rc = make_plan(ctx, params, max_block_len, &pl))) return rc;
     pl.warp = !pl.generic && choose_warp(ctx, n_blocks);
+    pl.split = !pl.generic && choose_split(ctx, n_blocks, pl.cls, max_block_len);
     DeviceState *d = find_dev(ctx, device);
     if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
     if (!d_in_offsets || !d_out_offsets || !d_status || (!d_out && out_capacity))
@@ -682,7 +728,7 @@ extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *str
     if ((rc = check_kind(ctx, model_kind))) return rc;
     Plan pl;
     if ((rc = make_plan(ctx, params, max_block_len, &pl))) return rc;
-    pl.warp = !pl.generic && choose_warp(ctx, n_blocks);
+    pl.warp = !pl.generic && choose_warp(ctx, n_blocks) && !(ctx->sched == REDUX_SCHED_AUTO && pl.cls == kNarrow);
     DeviceState *d = find_dev(ctx, device);
     if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
     if (n_blocks == 0) return REDUX_OK;
@@ -874,8 +920,9 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
     pl.warp = !pl.generic && choose_warp(ctx, sh.count);
-    // chunks of the generic path would share the Fenwick columns: one chunk
-    res->chunks = pl.generic ? std::vector<Shard>{{0, sh.count}} : make_chunks(sh.count, +1);
+    pl.split = !pl.generic && choose_split(ctx, sh.count, pl.cls, max_len);
+    // chunks of the generic path would share the Fenwick columns (and split chunks the range workspace): one chunk
+    res->chunks = (pl.generic || pl.split) ? std::vector<Shard>{{0, sh.count}} : make_chunks(sh.count, +1);
     const size_t nc = res->chunks.size();
     res->chunk_base.assign(nc, 0); res->chunk_total.assign(nc, 0);
     res->local_off.assign(sh.count + 1, 0);
@@ -1054,7 +1101,8 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     Plan pl;
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
-    pl.warp = !pl.generic && choose_warp(ctx, sh.count);
+    // small batches: the cooperating warp decodes 64-bit-product classes faster, a lone lane the narrow class
+    pl.warp = !pl.generic && choose_warp(ctx, sh.count) && !(ctx->sched == REDUX_SCHED_AUTO && pl.cls == kNarrow);
     const std::vector<Shard> chunks = pl.generic ? std::vector<Shard>{{0, sh.count}} : make_chunks(sh.count, -1);
     const size_t nc = chunks.size();
     CU_TRY(ctx, d->st_in.reserve(cbytes + 32));

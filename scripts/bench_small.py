@@ -1,7 +1,7 @@
 """Latency-bound configurations (BASELINE.json configs 1, 2, 5 in spirit): few long streams.
 The reference's corpora cannot travel to the GPU box, so the streams are text-like synthetic data of the
 same sizes: one 768,771 B stream (calgary/book1's size), the 29 Calgary+Canterbury file sizes, and
-12 blocks of <= 1 MiB.  Reports MB/s of raw input for both mappings and for the CPU oracle."""
+12 blocks of <= 1 MiB.  Reports MB/s of raw input for the three mappings (lane, warp, split encoder) and for the CPU oracle."""
 import json, os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -45,7 +45,7 @@ def main():
             model = rb.AdaptiveTreeModel(rb.Parameters(*params))
             row = {}
             ref = None
-            for sched, label in ((rb.SCHED_LANE, "lane"), (rb.SCHED_WARP, "warp")):
+            for sched, label in ((rb.SCHED_LANE, "lane"), (rb.SCHED_WARP, "warp"), (rb.SCHED_SPLIT, "split")):
                 te, td, comp, coff = run(ctx, sched, data, off, model)
                 row[label] = {"encode_MBps": round(data.size / te / 1e6, 2), "decode_MBps": round(data.size / td / 1e6, 2)}
                 if ref is None: ref = (comp.tobytes(), coff.tobytes())
@@ -55,7 +55,13 @@ def main():
             assert rc == 0
             want = b"".join(slots[int(so[i]):int(so[i]) + int(ol[i])].tobytes() for i in range(len(sizes)))
             assert want == ref[0], "GPU bytes differ from the oracle"
-            row["cpu_oracle"] = {"encode_MBps": round(data.size / tc / 1e6, 2), "threads": threads}
+            raw_off = off
+            comp_a = np.frombuffer(want, dtype=np.uint8)
+            coff_a = np.zeros(len(sizes) + 1, dtype=np.uint64); np.cumsum(ol, out=coff_a[1:])
+            t0 = time.perf_counter(); rc, back, rl, cons, st = o.decompress_batch(comp_a, coff_a, raw_off, o.TREE, params, threads); td_cpu = time.perf_counter() - t0
+            assert rc == 0 and (back == data).all()
+            row["cpu_oracle"] = {"encode_MBps": round(data.size / tc / 1e6, 2), "decode_MBps": round(data.size / td_cpu / 1e6, 2),
+                                 "threads": threads}
             res["%s %s" % (name, params)] = row
             print(name, params, json.dumps(row), flush=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_small.json"), "w"), indent=1)

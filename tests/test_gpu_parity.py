@@ -17,12 +17,13 @@ TRIPLES = [(8, 14, 16), (8, 22, 24), (8, 30, 32)]          # tests/corpora.rs:35
 KINDS = [(rb.AdaptiveLinearModel, o.LINEAR), (rb.AdaptiveTreeModel, o.TREE)]
 
 
-@pytest.fixture(scope="module", params=["lane", "warp"])
+@pytest.fixture(scope="module", params=["lane", "warp", "split"])
 def ctx(request):
-    """Every parity test runs on both stream-to-thread mappings: one stream per lane (Fenwick table in
-    shared memory) and one stream per warp (cumulative array in registers)."""
+    """Every parity test runs on all stream-to-thread mappings: one stream per lane (Fenwick table in
+    shared memory), one stream per warp (cumulative array in registers) and the split encoder (parallel
+    model phase + one coder warp per stream; its decode side is the warp mapping)."""
     c = rb.Context()
-    c.set_schedule(rb.SCHED_LANE if request.param == "lane" else rb.SCHED_WARP)
+    c.set_schedule({"lane": rb.SCHED_LANE, "warp": rb.SCHED_WARP, "split": rb.SCHED_SPLIT}[request.param])
     yield c
     c.close()
 
@@ -101,14 +102,14 @@ def test_auto_schedule_gives_the_same_bytes():
     off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
     model = rb.AdaptiveLinearModel(rb.Parameters(8, 22, 24))
     outs = []
-    for sched, count in ((rb.SCHED_AUTO, n), (rb.SCHED_AUTO, 100), (rb.SCHED_LANE, n), (rb.SCHED_WARP, n)):
+    for sched, count in ((rb.SCHED_AUTO, n), (rb.SCHED_AUTO, 100), (rb.SCHED_LANE, n), (rb.SCHED_WARP, n), (rb.SCHED_SPLIT, n)):
         with rb.Context() as c:
             c.set_schedule(sched)
             comp, coff, st = c.encode_batch(raw[:count * L], off[:count + 1], model)
             back, lens, cons, st = c.decode_batch(comp, coff, off[:count + 1], model)
             assert (back == raw[:count * L]).all()
             outs.append((comp.tobytes(), coff.tobytes()))
-    assert outs[0] == outs[2] == outs[3]
+    assert outs[0] == outs[2] == outs[3] == outs[4]
     assert outs[2][0].startswith(outs[1][0])
 
 
