@@ -123,39 +123,116 @@ split_model_kernel(const SplitJob job)
     if (lane < tail) out[end - tail + lane] = mine;
 }
 
-// ---- B: the serial coder chain, one warp per stream (state warp-uniform, lane 0 stores)
-struct WarpBitSink2 : BitSink2 {
-    bool en;
-    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {
-        acc = (acc << n) | v;
-        nb += n;
-        const bool full = nb >= 32;                                // predicated, no branch on the chain
-        const uint32_t word = __byte_perm((uint32_t)(acc >> (nb & 31)), 0, 0x0123);
-        if (full && en) w0[wi] = word;
-        wi += full ? 1u : 0u;
-        nb &= 31u;
+// ---- B: the serial coder chain, one warp per stream.
+// The chain itself is only the range update and the closed-form renormalisation (every lane computes it;
+// the state is warp-uniform).  What a step emits -- the n1 settled bits and its E3 count k -- is LATCHED
+// by the lane whose index equals the step's position in the round, and the 32 steps of a round are packed
+// by the whole warp at once (RoundPacker): pending runs by a segmented sum, bit offsets by a prefix sum,
+// the bits ORed into a shared staging window and stored as whole big-endian words, coalesced.  No
+// branch, store or packer state sits between two steps of the chain.
+struct RoundPacker {
+    uint32_t *stage;        // shared: [kStageWords], word 0 starts with the `cb` carried bits
+    uint32_t *w0;           // output slot (16-byte aligned)
+    uint32_t wi, cb, pend;  // words stored so far, carried bits (< 32), pending E3 run -- all warp-uniform
+    uint32_t lane;
+    static constexpr int kStageWords = 40;      // 31 carried bits + 32 steps x 32 bits + slack
+
+    __device__ __forceinline__ void init(uint32_t *smem, uint8_t *slot, uint32_t l) {
+        stage = smem; w0 = (uint32_t *)slot; wi = 0; cb = 0; pend = 0; lane = l;
+        for (int i = (int)l; i < kStageWords; i += 32) stage[i] = 0;
+        __syncwarp();
     }
-    __device__ __forceinline__ uint32_t put_code(uint32_t bits, uint32_t n1, uint32_t pend, uint32_t k) {
-        const bool emit = n1 != 0;
-        const uint32_t n = emit ? n1 + pend : 0u;
-        if (n > 32) {
+    // stores the complete words of the window, keeps the partial one as the new carry
+    __device__ __forceinline__ void drain(uint32_t total_bits) {
+        __syncwarp();
+        const uint32_t full = total_bits >> 5;
+        const uint32_t carry = stage[full];
+        for (uint32_t i = lane; i < full; i += 32) w0[wi + i] = __byte_perm(stage[i], 0, 0x0123);
+        __syncwarp();
+        for (int i = (int)lane; i < kStageWords; i += 32) stage[i] = 0;
+        __syncwarp();
+        if (lane == 0) stage[0] = carry;
+        __syncwarp();
+        wi += full; cb = total_bits & 31;
+    }
+    // warp-uniform append of the low `len` (<= 32) bits of v at the end of the window
+    __device__ __forceinline__ void append_uniform(uint32_t v, uint32_t len) {
+        if (len == 0) return;
+        const uint64_t x = (uint64_t)v << (64 - len - cb);
+        if (lane == 0) { stage[0] |= (uint32_t)(x >> 32); stage[1] |= (uint32_t)x; }
+        drain(cb + len);
+    }
+    // put_bit semantics (src/codec.rs:39-46) for one step, warp-uniform, any run length
+    __device__ __forceinline__ void step_uniform(uint32_t bits, uint32_t n1, uint32_t k) {
+        if (n1) {
             const uint32_t b = (bits >> (n1 - 1)) & 1u;
-            put(b, 1);
-            while (pend > 0) {
-                const uint32_t m = pend < 32 ? pend : 32;
-                put(b ? 0u : (0xFFFFFFFFu >> (32 - m)), m);
-                pend -= m;
+            append_uniform(b, 1);
+            for (uint32_t left = pend; left > 0;) {
+                const uint32_t m = left < 32 ? left : 32;
+                append_uniform(b ? 0u : (0xFFFFFFFFu >> (32 - m)), m);
+                left -= m;
             }
-            if (n1 > 1) put(bits & (0xFFFFFFFFu >> (33 - n1)), n1 - 1);
+            if (n1 > 1) append_uniform(bits & (0xFFFFFFFFu >> (33 - n1)), n1 - 1);
+            pend = k;
         } else {
-            put(bits + __funnelshift_lc(0u, 1u, n - 1u) - __funnelshift_lc(0u, 1u, n1 - 1u), n);
+            pend += k;
         }
-        return (emit ? 0u : pend) + k;
     }
+    // One round: lane i < m holds step i's (bits, n1, k); lanes >= m must hold n1 = k = 0.
+    __device__ __forceinline__ void round(uint32_t bits, uint32_t n1, uint32_t k) {
+        // pending run in front of every step: k summed since the last emitting step (segmented sum)
+        uint32_t S = k;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFullMask, S, d);
+            if (lane >= (uint32_t)d) S += y;
+        }
+        const uint32_t Sprev = S - k;                              // sum of k over the steps before mine
+        const uint32_t emask = __ballot_sync(kFullMask, n1 != 0);
+        const uint32_t below = emask & ((1u << lane) - 1u);
+        const uint32_t le = below ? 31u - (uint32_t)__clz((int)below) : 0u;
+        const uint32_t Sle = __shfl_sync(kFullMask, Sprev, (int)le);
+        const uint32_t pb = below ? Sprev - Sle : pend + Sprev;
+        const uint32_t n = n1 ? n1 + pb : 0u;
+        // pending run left behind by the round
+        const uint32_t S31 = __shfl_sync(kFullMask, S, 31);
+        const uint32_t last = emask ? 31u - (uint32_t)__clz((int)emask) : 0u;
+        const uint32_t Slast = __shfl_sync(kFullMask, Sprev, (int)last);
+        const uint32_t pend_out = emask ? S31 - Slast : pend + S31;
+        if (__any_sync(kFullMask, n > 32)) {
+            // a long E3 run (rare): step by step, warp-uniform
+            for (int i = 0; i < 32; ++i) {
+                const uint32_t bi = __shfl_sync(kFullMask, bits, i), ni = __shfl_sync(kFullMask, n1, i);
+                const uint32_t ki = __shfl_sync(kFullMask, k, i);
+                step_uniform(bi, ni, ki);
+            }
+            return;
+        }
+        // bit offsets: exclusive prefix sum of n
+        uint32_t O = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(kFullMask, O, d);
+            if (lane >= (uint32_t)d) O += y;
+        }
+        const uint32_t total = __shfl_sync(kFullMask, O, 31);
+        O -= n;
+        if (n) {
+            // [b][pb x !b][rest] as one number: bits + 2^(n-1) - 2^(n1-1) (see BitSink2::put_code)
+            const uint32_t v = bits + (1u << (n - 1)) - (1u << (n1 - 1));
+            const uint32_t at = cb + O;
+            const uint64_t x = (uint64_t)v << (64 - n - (at & 31));
+            atomicOr(&stage[at >> 5], (uint32_t)(x >> 32));
+            if ((uint32_t)x) atomicOr(&stage[(at >> 5) + 1], (uint32_t)x);
+        }
+        pend = pend_out;
+        drain(cb + total);
+    }
+    // flush_bits (src/bitio/mod.rs:183-198): the last partial word, zero padded; returns the byte count
     __device__ __forceinline__ uint32_t finish() {
-        const uint32_t bytes = wi * 4 + (nb + 7) / 8;
-        if (nb && en) w0[wi] = __byte_perm((uint32_t)(acc << (32 - nb)), 0, 0x0123);
-        return bytes;
+        __syncwarp();
+        if (cb && lane == 0) w0[wi] = __byte_perm(stage[0], 0, 0x0123);
+        return wi * 4 + (cb + 7) / 8;
     }
 };
 
@@ -163,9 +240,9 @@ struct WarpBitSink2 : BitSink2 {
 // shifts double low and high alike, so range' = (quotient_hi - quotient_lo) << shifts is known two
 // operations after the shift count, without waiting for the new low/high registers.
 template <int CLS, bool C32>
-__device__ __forceinline__ uint32_t split_step(uint32_t &L, uint32_t &rm1, uint32_t &pend, WarpBitSink2 &sink,
-                                               uint32_t cl, uint32_t ch, uint32_t count,
-                                               const typename Cls<CLS>::M &g, uint32_t one)
+__device__ __forceinline__ void split_step(uint32_t &L, uint32_t &rm1, uint32_t cl, uint32_t ch, uint32_t count,
+                                           const typename Cls<CLS>::M &g, uint32_t one,
+                                           uint32_t &bits, uint32_t &n1, uint32_t &k)
 {
     using C = Cls<CLS>;
     using P = typename C::P;
@@ -173,13 +250,12 @@ __device__ __forceinline__ uint32_t split_step(uint32_t &L, uint32_t &rm1, uint3
     const uint32_t qh = (uint32_t)C::divc(nh, g, count), ql = (uint32_t)C::divc(nl, g, count);
     const uint32_t nh2 = ~(qh * one + (L - 1u));
     const uint32_t l2 = ql * one + L;
-    const uint32_t n1 = common_prefix<C32>(~(l2 ^ nh2));
-    const uint32_t k = clz_nz(~shl_c((l2 & nh2) << 1, n1));
+    n1 = common_prefix<C32>(~(l2 ^ nh2));
+    k = clz_nz(~shl_c((l2 & nh2) << 1, n1));
     const uint32_t n = n1 + k;
     rm1 = shl_c(qh - ql, n) - 1u;                                  // (high' - low' + 1) << n, minus one
-    pend = sink.put_code(top_bits(l2, n1), n1, pend, k);
+    bits = top_bits(l2, n1);
     L = shl_c(l2, n) & 0x7FFFFFFFu;
-    return n;
 }
 
 template <int CLS, bool C32>
@@ -188,6 +264,7 @@ split_coder_kernel(const LaneEncJob job, const SplitJob sj)
 {
     using C = Cls<CLS>;
     using M = typename C::M;
+    __shared__ uint32_t stage[RoundPacker::kStageWords];
     const uint32_t lane = threadIdx.x;
     const uint64_t blk = blockIdx.x;
     const uint64_t off = job.in_off[blk];
@@ -195,15 +272,13 @@ split_coder_kernel(const LaneEncJob job, const SplitJob sj)
     const uint32_t c = job.c, one = job.one, tcap = job.tcap;
     const M *magic = reinterpret_cast<const M *>(job.magic);
     const uint2 *pairs = sj.pairs + blk * sj.pair_stride;
-    WarpBitSink2 sink;
-    sink.init(job.slots + blk * job.slot_stride);
-    sink.en = lane == 0;
+    RoundPacker pk;
+    pk.init(stage, job.slots + blk * job.slot_stride, lane);
     const uint32_t maxv = c == 32 ? 0xFFFFFFFFu : ((1u << c) - 1u);
-    uint32_t L = 0, rm1 = maxv, pend = 0;                          // low = 0, range - 1 = code_max (src/codec.rs:30-31)
+    uint32_t L = 0, rm1 = maxv;                                    // low = 0, range - 1 = code_max (src/codec.rs:30-31)
 
     // 32 positions per round: lane l fetches the range and the reciprocal of position base + l (one round
-    // ahead); the serial chain takes them from the lanes by shuffle, one STEP ahead, so that neither the
-    // loads nor the shuffles sit on the chain
+    // ahead); the chain takes them from the lanes by shuffle, one STEP ahead
     auto fetch_pair = [&](uint32_t base) {
         const uint32_t t = base + lane;
         return t < len ? pairs[t] : make_uint2(0, 1);
@@ -224,7 +299,8 @@ split_coder_kernel(const LaneEncJob job, const SplitJob sj)
         M g_n = g;
         g_n.m = __shfl_sync(kFullMask, g.m, 0);
         g_n.sh = __shfl_sync(kFullMask, g.sh, 0);
-#pragma unroll 2
+        uint32_t my_bits = 0, my_n1 = 0, my_k = 0;
+#pragma unroll 4
         for (uint32_t i = 0; i < m; ++i) {
             const uint32_t cl = cl_n, ch = ch_n;
             const M gi = g_n;
@@ -233,16 +309,24 @@ split_coder_kernel(const LaneEncJob job, const SplitJob sj)
             g_n.m = __shfl_sync(kFullMask, g.m, nx);
             g_n.sh = __shfl_sync(kFullMask, g.sh, nx);
             const uint32_t t = base + i;
-            split_step<CLS, C32>(L, rm1, pend, sink, cl, ch, kNsym + (t < tcap ? t : tcap), gi, one);
+            uint32_t bits, n1, k;
+            split_step<CLS, C32>(L, rm1, cl, ch, kNsym + (t < tcap ? t : tcap), gi, one, bits, n1, k);
+            const bool mine = lane == i;
+            my_bits = mine ? bits : my_bits; my_n1 = mine ? n1 : my_n1; my_k = mine ? k : my_k;
         }
+        pk.round(my_bits, my_n1, my_k);
     }
+    // EOF symbol: cum(256) = total - 1; then the tail of src/codec.rs:91-99: the remaining `extra` MSBs of
+    // low, the first of them carrying the pending run
     const uint32_t tt = len < tcap ? len : tcap;
     const uint32_t countf = kNsym + tt;
     const M gf = C::ldm(magic + tt);
-    const uint32_t shifts = split_step<CLS, C32>(L, rm1, pend, sink, countf - 1, countf, countf, gf, one);
-    const uint32_t extra = c - shifts;                             // src/codec.rs:91-99
-    sink.put_code(top_bits(L, extra), extra, pend, 0);
-    const uint32_t bytes = sink.finish();
+    uint32_t bits, n1, k;
+    split_step<CLS, C32>(L, rm1, countf - 1, countf, countf, gf, one, bits, n1, k);
+    pk.step_uniform(bits, n1, k);
+    const uint32_t extra = c - (n1 + k);
+    pk.step_uniform(top_bits(L, extra), extra, 0);
+    const uint32_t bytes = pk.finish();
     if (lane == 0) { job.sizes[blk] = bytes; job.status[blk] = 0; }
 }
 
