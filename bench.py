@@ -312,8 +312,9 @@ def run_ours(a):
     kdur = {k: (v[0] / v[1] * 1e-3 if v[1] else None) for k, v in ktimes.items()}
     dom = "decode" if (kdur.get("decode") or 0) >= (kdur.get("encode") or 0) else "encode"
     achieved = alg_bytes / kdur[dom] / 1e9
-    ncu, ncu_src = ncu_capture(workload_name(a), dom + "_lane_kernel")
-    roofline = {"bound": "hbm", "kernel": dom + "_lane_kernel", "achieved": round(achieved, 2), "peak": peak,
+    kname = dom + ("_lane_al_kernel" if params[2] <= 32 else "_lane_kernel")
+    ncu, ncu_src = ncu_capture(workload_name(a), kname)
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 2), "peak": peak,
                 "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": ncu["traffic"] if ncu else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": {k: (round(v * 1e3, 3) if v else None) for k, v in kdur.items()},
