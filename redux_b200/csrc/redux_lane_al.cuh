@@ -228,6 +228,59 @@ struct BitSink2 {
     }
 };
 
+// ------------------------------------------------------------------ byte source (encoder input), v2
+// 16 raw bytes per refill, prefetched one chunk ahead.  The chunk is fetched as four independent 32-bit
+// loads: with one 128-bit load the register allocator kept the consumer's word register inside the load's
+// destination quad and copied the FRESH value out right after issuing the load, i.e. every refill waited
+// a full memory latency (7 % of the encoder's stall samples in profiles/r01_final2_*).
+struct ByteSource2 {
+    const uint32_t *base;   // 16-byte aligned start of the stream's first chunk
+    uint32_t ci, clast;     // next chunk to prefetch / last chunk that may be read
+    uint32_t n0, n1, n2, n3;
+    uint32_t w, x, y, z;    // current word (already shifted) and the following words of the chunk
+    uint32_t pos;           // byte position (chunk-relative phase in the low 4 bits)
+
+    __device__ __forceinline__ void fetch(uint32_t c) {
+        const uint32_t *q = base + (size_t)(c < clast ? c : clast) * 4;   // past the end: re-read, never consumed
+        n0 = __ldg(q); n1 = __ldg(q + 1); n2 = __ldg(q + 2); n3 = __ldg(q + 3);
+    }
+    __device__ __forceinline__ void init(const uint8_t *src, uint32_t len) {
+        const uintptr_t a = (uintptr_t)src;
+        base = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)15);
+        pos = (uint32_t)(a & 15);
+        clast = len ? (pos + len - 1) >> 4 : 0;
+        n0 = n1 = n2 = n3 = 0;
+        uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        if (len) {                          // len == 0: next() is never called, nothing is loaded
+            fetch(0);
+            q0 = n0; q1 = n1; q2 = n2; q3 = n3;
+            fetch(1);
+        }
+        ci = 2;
+        const uint32_t ws = pos >> 2;
+        w = ws == 0 ? q0 : ws == 1 ? q1 : ws == 2 ? q2 : q3;
+        x = ws == 0 ? q1 : ws == 1 ? q2 : q3;
+        y = ws == 0 ? q2 : q3;
+        z = q3;
+        w >>= 8 * (pos & 3);
+    }
+    __device__ __forceinline__ uint32_t next() {
+        const uint32_t sym = w & 0xFFu;
+        w >>= 8;
+        ++pos;
+        if ((pos & 3) == 0) {
+            if ((pos & 15) == 0) {
+                w = n0; x = n1; y = n2; z = n3;
+                fetch(ci);
+                ++ci;
+            } else {
+                w = x; x = y; y = z;
+            }
+        }
+        return sym;
+    }
+};
+
 // One coding step on left-aligned state (src/codec.rs:55-89).  L: low << sh, H: (high << sh) | ones.
 // Returns the number of shifts.
 template <int CLS, bool C32>
@@ -273,7 +326,7 @@ encode_lane_al_kernel(const LaneEncJob job)
     const M *magic = reinterpret_cast<const M *>(job.magic);
     const uint32_t tcap = job.tcap;
 
-    ByteSource src;
+    ByteSource2 src;
     src.init(job.in + off, len);
     BitSink2 sink;
     sink.init(job.slots + blk * job.slot_stride);

@@ -388,3 +388,33 @@ def test_generic_many_blocks_share_columns(ctx):
         assert out[int(out_off[i]):int(out_off[i + 1])].tobytes() == o.compress(raw[i * L:(i + 1) * L], o.TREE, params)[1]
     back, lens, cons, status = ctx.decode_batch(out, out_off, off, model)
     assert (status == 0).all() and (back[: n * L] == raw).all()      # 96 bytes = 64 whole 12-bit symbols
+
+
+def test_multi_device_context_shards_by_block_ranges():
+    """one context over all visible GPUs, one host thread per device, contiguous block ranges,
+    no collective.  The bytes, offsets and statuses must not depend on the number of devices.  Needs >= 2 GPUs
+    (skipped on a 1-GPU box; `gpurun --gpus 2` runs it)."""
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n, L = 3001, 2500                                   # odd count: uneven shards
+    raw = rb.generate_blocks_host(0, n, L, SEED)
+    lens = np.full(n, L, dtype=np.uint64); lens[::7] = 0; lens[5::11] = 17      # ragged, some empty
+    off = np.zeros(n + 1, dtype=np.uint64); np.cumsum(lens, out=off[1:])
+    data = np.concatenate([raw[i * L:i * L + int(lens[i])] for i in range(n)])
+    for params in ((8, 14, 16), (8, 30, 32), (12, 22, 24)):
+        model = rb.AdaptiveTreeModel(rb.Parameters(*params))
+        with rb.Context([0]) as one:
+            ref_comp, ref_off, ref_st = one.encode_batch(data, off, model)
+        with rb.Context(list(range(ng))) as many:
+            assert many.device_count == ng
+            comp, coff, st = many.encode_batch(data, off, model)
+            assert comp.tobytes() == ref_comp.tobytes() and (coff == ref_off).all() and (st == 0).all()
+            back, rl, cons, st = many.decode_batch(comp, coff, off, model)
+            assert (st == 0).all() and (cons == coff[1:] - coff[:-1]).all()
+            if params[0] == 8:
+                assert (rl == lens).all() and (back[: int(off[-1])] == data).all()
+        for i in (0, 1, 2, 1500, 3000):
+            b = data[int(off[i]):int(off[i + 1])]
+            assert comp[int(coff[i]):int(coff[i + 1])].tobytes() == o.compress(b, o.TREE, params)[1], (params, i)
