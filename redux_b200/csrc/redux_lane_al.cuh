@@ -405,6 +405,9 @@ struct BitWindow {
     }
 };
 
+// Largest total frequency for which the float estimate of value = X / range is within one of the quotient.
+constexpr uint32_t kQuotientMaxCount = 1u << 20;
+
 // ------------------------------------------------------------------ decoder
 template <typename TW, int CLS, bool FULL, bool C32>
 struct LaneDecoderAl {
@@ -464,7 +467,8 @@ struct LaneDecoderAl {
                     plo = r2 ? p2 : base;
                     I += (ra ? (uint32_t)(m << 5) : 0u) + (r2 ? (uint32_t)(h << 5) : 0u);
                 }
-            } else {
+            } else if (count > kQuotientMaxCount) {
+                // 64-bit products, very long streams: the plain product-domain descent
 #pragma unroll
                 for (int m = 128; m >= 2; m >>= 1) {              // even nodes i + m
                     const uint32_t tv = (FULL ? 0u : (uint32_t)m) + tab.t[I + (uint32_t)(m << 5)];
@@ -478,6 +482,34 @@ struct LaneDecoderAl {
                     const bool right = X >= p;
                     if (right) { I += 32u; plo = p; } else { phi = p; }
                 }
+            } else {
+                // 64-bit products: get the reference's value = X / range (src/codec.rs:131) FIRST -- a float
+                // estimate made exact by one remainder check -- and search in the 32-bit value domain, two
+                // tree levels per round like the narrow class.  The estimate is within one of the quotient
+                // because the quotient is < count <= 2^20: relative error 2^-24 (X) + 2^-24 (range) + 2^-22
+                // (division) keeps the absolute error below 0.4.
+                uint32_t v = (uint32_t)__fdividef(__ull2float_rn((unsigned long long)X), (float)rm1 + 1.0f);
+                const P pv = C::mulr(v, rm1);                     // v * range
+                if (pv > X) v -= 1u;                              // estimate one too high
+                else if (X - pv > (P)rm1) v += 1u;                // one too low (remainder >= range)
+                uint32_t lo = 0, hi = count - 1;                  // cum(i) <= v < hi tracked in the value domain
+#pragma unroll
+                for (int m = 128; m >= 2; m >>= 2) {
+                    const int h = m >> 1;
+                    const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;
+                    const uint32_t a = lo + (FULL ? 0u : (uint32_t)m) + tab.t[I + (uint32_t)(m << 5)];
+                    const uint32_t b = lo + (FULL ? 0u : (uint32_t)h) + tab.t[(int)I + (h << 5) + oddadj];
+                    const uint32_t cc = a + (FULL ? 0u : (uint32_t)h) + tab.t[(int)I + ((m + h) << 5) + oddadj];
+                    const bool ra = v >= a, rb = v >= b, rc = v >= cc;
+                    const bool r2 = ra ? rc : rb;
+                    const uint32_t p2 = ra ? cc : b;
+                    const uint32_t base = ra ? a : lo;
+                    hi = r2 ? (ra ? hi : a) : p2;
+                    lo = r2 ? p2 : base;
+                    I += (ra ? (uint32_t)(m << 5) : 0u) + (r2 ? (uint32_t)(h << 5) : 0u);
+                }
+                plo = C::mulr(lo, rm1);
+                phi = C::mulr(hi, rm1);
             }
             if (is_eof) {                                         // src/codec.rs:136-138: no renorm, no reads
                 st = -1;

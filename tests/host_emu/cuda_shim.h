@@ -67,5 +67,7 @@ static inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t sh)
     if (sh >= 32) return hi;
     return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
 }
+static inline float __fdividef(float a, float b) { return a / b; }
+static inline float __ull2float_rn(unsigned long long x) { return (float)x; }
 static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }

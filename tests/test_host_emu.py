@@ -367,3 +367,18 @@ def test_generic_truncated_and_full(emu):
         cap = max(0, (len(blocks[i]) * 8 // 12 * 12) // 8 - 1)
         rc, out, ic, oc = o.decompress(s, o.TREE, params, out_cap=cap)
         assert rc == o.IO_ERROR and int(status[i]) == 6 and outs[i] == out, (i, rc, int(status[i]))
+
+
+def test_wide_decoder_quotient_estimate_and_its_fallback(emu):
+    """The wide-class decoder derives value = X / range from a float estimate while count <= 2^20 and
+    falls back to the product-domain descent beyond: a 1.1 MB block crosses that boundary."""
+    rng = np.random.default_rng(31)
+    big = np.concatenate([rng.integers(0, 256, 400000, dtype=np.uint8),
+                          rng.choice(np.frombuffer(b"acgt", dtype=np.uint8), 400000),
+                          np.minimum(rng.geometric(0.3, 350000) - 1, 255).astype(np.uint8)]).tobytes()
+    for f, c in ((22, 24), (30, 32)):
+        rc, want, ic, oc = o.compress(big, o.TREE, (8, f, c))
+        assert rc == o.OK
+        assert emu_encode(emu, [big, b"abc"], f, c)[0] == want
+        outs, raw_len, consumed, status = emu_decode(emu, [want], [len(big)], f, c)
+        assert int(status[0]) == 0 and outs[0] == big and int(consumed[0]) == len(want)
