@@ -335,9 +335,10 @@ void launch_encode_warp(int cls, const LaneEncJob &job, cudaStream_t s)
 void launch_decode_warp(int cls, const LaneDecJob &job, cudaStream_t s)
 {
     const uint32_t grid = (uint32_t)((job.n_blocks + kWarpCtaWarps - 1) / kWarpCtaWarps);
-    if (cls == kNarrow)    decode_warp_kernel<kNarrow><<<grid, kWarpCtaThreads, 0, s>>>(job);
-    else if (cls == kWide) decode_warp_kernel<kWide><<<grid, kWarpCtaThreads, 0, s>>>(job);
-    else                   decode_warp_kernel<kHuge><<<grid, kWarpCtaThreads, 0, s>>>(job);
+    if (cls == kNarrow)     decode_warp_al_kernel<kNarrow, false><<<grid, kWarpCtaThreads, 0, s>>>(job);
+    else if (cls == kHuge)  decode_warp_kernel<kHuge><<<grid, kWarpCtaThreads, 0, s>>>(job);
+    else if (job.c == 32)   decode_warp_al_kernel<kWide, true><<<grid, kWarpCtaThreads, 0, s>>>(job);
+    else                    decode_warp_al_kernel<kWide, false><<<grid, kWarpCtaThreads, 0, s>>>(job);
 }
 
 // Split encoder: model phase over all chunks of all streams, then one coder warp per stream.

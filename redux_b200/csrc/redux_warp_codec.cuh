@@ -19,6 +19,7 @@
 #pragma once
 #include "redux_common.cuh"
 #include "redux_lane_codec.cuh"
+#include "redux_lane_al.cuh"
 
 namespace rdx {
 
@@ -321,6 +322,117 @@ decode_warp_kernel(const LaneDecJob job)
         job.raw_len[blk] = d.t;
         job.consumed[blk] = (d.src.used() + 7) >> 3;
         job.status[blk] = d.st < 0 ? 0 : d.st;
+    }
+}
+
+// ------------------------------------------------------------------ decoder, code_bits <= 32 (tuned)
+// Same mapping (one stream per warp, cumulative array of AdaptiveLinearModel in registers, coder state
+// warp-uniform) with the coder of redux_lane_al.cuh -- left-aligned low/high, the code value as a bit
+// window, FLO.SH renormalisation -- and a search that is off the multiplier:
+//   * value = ((pending-low+1)*count - 1) / range (src/codec.rs:131) comes from a float estimate made
+//     exact by one remainder check (the quotient is < count <= 2^20; beyond that an exact 64-bit division);
+//   * every lane compares its 8 cumulative entries with the value (get_symbol, adaptive_linear.rs:61-70);
+//     cum_lo is the warp maximum of the entries <= value, cum_hi the warp minimum of the entries > value
+//     (bounded by cum(256) = count - 1): two redux.sync the narrowing waits for, while the symbol itself
+//     (a third one, the count of entries <= value) is only needed by the model update and the output.
+template <int CLS, bool C32>
+__global__ void __launch_bounds__(kWarpCtaThreads)
+decode_warp_al_kernel(const LaneDecJob job)
+{
+    using C = Cls<CLS>;
+    using P = typename C::P;
+    using M = typename C::M;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t blk = (uint64_t)blockIdx.x * kWarpCtaWarps + (threadIdx.x >> 5);
+    if (blk >= job.n_blocks) return;                               // warp-uniform
+
+    const uint64_t coff = job.comp_off[blk];
+    const uint64_t clen = job.comp_off[blk + 1] - coff;
+    const uint64_t roff = job.raw_off[blk];
+    const uint64_t cap64 = job.raw_off[blk + 1] - roff;
+    if (clen >= (1ull << 29)) {
+        if (lane == 0) { job.raw_len[blk] = 0; job.consumed[blk] = 0; job.status[blk] = 5; }
+        return;
+    }
+    const uint32_t c = job.c, sh = 32 - c, one = job.one, tcap = job.tcap;
+    const uint32_t cap = cap64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)cap64;
+    const uint32_t total_bits = (uint32_t)clen * 8;
+    const M *magic = reinterpret_cast<const M *>(job.magic);
+
+    uint32_t cum[8];                                               // cum(lane + 32 j); a fresh model: cum(i) = i
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cum[j] = lane + 32u * j;
+    BitWindow bw;
+    WarpByteSink out;
+    out.init(job.raw + roff);
+    out.en = lane == 0;
+    uint32_t L = 0, H = 0xFFFFFFFFu, V = 0, left = 0, t = 0;
+    int32_t st = 0;
+    if (total_bits < c) {                                          // src/codec.rs:124-127
+        st = 1;
+    } else {
+        V = bw.init(job.comp + coff, (uint32_t)clen);
+        left = total_bits - c;
+    }
+    M gn = C::ldm(magic);
+    while (st == 0) {
+        const uint32_t tt = t < tcap ? t : tcap;                   // updates so far
+        const uint32_t count = kNsym + tt;
+        const M g = gn;
+        gn = C::ldm(magic + (t + 1 < tcap ? t + 1 : tcap));
+        const uint32_t rm1 = (H - L) >> sh;
+        const P X = C::mulr(count, (V - L) >> sh) - 1;
+        // value = X / range
+        uint32_t v;
+        if (count <= kQuotientMaxCount) {
+            v = (uint32_t)__fdividef(CLS == kNarrow ? __uint2float_rn((uint32_t)X) : __ull2float_rn((unsigned long long)X),
+                                     (float)rm1 + 1.0f);
+            const P pv = C::mulr(v, rm1);
+            if (pv > X) v -= 1u;
+            else if (X - pv > (P)rm1) v += 1u;
+        } else {
+            v = (uint32_t)((unsigned long long)X / ((unsigned long long)rm1 + 1ull));
+        }
+        if (v >= count - 1) { st = -1; break; }                    // EOF symbol (src/codec.rs:136-138)
+        uint32_t below = 0, lo = 0, hi = count - 1;                // entries <= value; their max; min of the rest
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool le = cum[j] <= v;
+            below += le ? 1u : 0u;
+            lo = max(lo, le ? cum[j] : 0u);
+            hi = min(hi, le ? 0xFFFFFFFFu : cum[j]);
+        }
+        const uint32_t cl = __reduce_max_sync(kFullMask, lo);
+        const uint32_t ch = __reduce_min_sync(kFullMask, hi);
+        const uint32_t sym = __reduce_add_sync(kFullMask, below) - 1u;     // cum(0) = 0 always counts
+        // src/codec.rs:133-134 and :140-158 in closed form
+        const uint32_t nh2 = ~((uint32_t)C::divc(C::mulr(ch, rm1), g, count) * one + (L - 1u));
+        const uint32_t l2 = (uint32_t)C::divc(C::mulr(cl, rm1), g, count) * one + L;
+        const uint32_t n1 = common_prefix<C32>(~(l2 ^ nh2));
+        const uint32_t k = clz_nz(~shl_c((l2 & nh2) << 1, n1));
+        const uint32_t n = n1 + k;
+        if (n > left) { st = 1; left = 0; break; }                 // Err(Eof) inside get_bit (:49-52)
+        if (t >= cap) { st = 6; break; }                           // sink full
+        left -= n;
+        const uint32_t win = bw.win();
+        const uint32_t A = __funnelshift_lc(win, V, n1);
+        const uint32_t Bv = __funnelshift_lc(shl_c(win, n1), A, k);
+        V = (A & 0x80000000u) | (Bv & 0x7FFFFFFFu);
+        bw.advance(n);
+        L = shl_c(l2, n) & 0x7FFFFFFFu;
+        H = ~shl_c(nh2, n) | 0x80000000u;
+        if (t < tcap) {                                            // adaptive_linear.rs:33-39, frozen at freq_max
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cum[j] += (lane + 32u * j > sym) ? 1u : 0u;
+        }
+        out.put(sym);
+        ++t;
+    }
+    out.finish();
+    if (lane == 0) {
+        job.raw_len[blk] = t;
+        job.consumed[blk] = (total_bits - left + 7) >> 3;
+        job.status[blk] = st < 0 ? 0 : st;
     }
 }
 
