@@ -232,7 +232,7 @@ struct BitSink2 {
 // 16 raw bytes per refill, prefetched one chunk ahead.  The chunk is fetched as four independent 32-bit
 // loads: with one 128-bit load the register allocator kept the consumer's word register inside the load's
 // destination quad and copied the FRESH value out right after issuing the load, i.e. every refill waited
-// a full memory latency (7 % of the encoder's stall samples in profiles/r01_final2_*).
+// a full memory latency (7 % of the encoder's stall samples in profiles/r01_final_ncu_full_summary.md era captures).
 struct ByteSource2 {
     const uint32_t *base;   // 16-byte aligned start of the stream's first chunk
     uint32_t ci, clast;     // next chunk to prefetch / last chunk that may be read

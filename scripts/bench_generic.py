@@ -13,7 +13,6 @@ off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
 ctx = rb.Context([0])
 res = {}
 cases = [("s=4 (4,10,16)", (4, 10, 16), None), ("s=12 (12,22,24)", (12, 22, 24), None), ("s=16 (16,18,20)", (16, 18, 20), None),
-         ("s=8 pre-trained (8,14,16)", (8, 14, 16), [int(x) for x in raw[:4000]]), ("s=8 fresh, tuned kernels (8,14,16)", (8, 14, 16), None)]
 for name, params, train in cases:
     model = rb.AdaptiveTreeModel(rb.Parameters(*params))
     if train: model.train(train)
