@@ -154,11 +154,33 @@ def make_kat():
         for p in triples:
             vecs.append({"name": "%s-%d" % (kind, n), "params": list(p), "input": data.hex(),
                          "compressed": PyCoder(*p).encode(data).hex(), "source": "PyCoder"})
-    # non-byte symbol widths (oracle only; the device path is scoped to symbol_bits == 8)
+    # non-byte symbol widths
     for s, f, c in [(4, 10, 16), (4, 14, 16), (12, 14, 16), (12, 24, 30), (3, 5, 7), (1, 3, 5)]:
         data = gen("uniform", 150, 0x5EED1000 + s)
         vecs.append({"name": "sym%d" % s, "params": [s, f, c], "input": data.hex(),
                      "compressed": PyCoder(s, f, c).encode(data).hex(), "source": "PyCoder"})
+    # more widths (the device's generic path): lengths that leave a partial trailing symbol, frozen regimes
+    for s, f, c in [(4, 10, 16), (12, 14, 16), (12, 30, 32), (5, 8, 11), (7, 20, 40), (16, 18, 20), (2, 4, 6), (9, 11, 13)]:
+        for kind, n in (("skew", 301), ("runs", 1000), ("uniform", 7)):
+            data = gen(kind, n, 0x5EED2000 + 16 * s + n)
+            vecs.append({"name": "sym%d-%s-%d" % (s, kind, n), "params": [s, f, c], "input": data.hex(),
+                         "compressed": PyCoder(s, f, c).encode(data).hex(), "source": "PyCoder"})
+    # models trained before the call: get_frequency(sym) for sym in train, then compress (src/model/mod.rs:23-25)
+    for (s, f, c), ntrain in [((8, 14, 16), 40), ((8, 10, 12), 2000), ((8, 30, 32), 500), ((4, 10, 16), 100),
+                              ((12, 22, 24), 300)]:
+        st = 0x5EED3000 + s * 1000 + ntrain
+        train = []
+        for _ in range(ntrain):
+            st, r = splitmix64(st)
+            train.append((r >> 40) % min((1 << s) + 1, 48))       # skewed towards small symbols, may include EOF-range
+        for kind, n in (("skew", 400), ("runs", 700), ("uniform", 0)):
+            data = gen(kind, n, 0x5EED4000 + s + n)
+            coder = PyCoder(s, f, c)
+            for sym in train:
+                coder._lookup_then_update(sym)
+            vecs.append({"name": "trained%d-%s-%d" % (ntrain, kind, n), "params": [s, f, c], "input": data.hex(),
+                         "train": bytes(train).hex(), "compressed": coder.encode(data).hex(),
+                         "source": "PyCoder, pre-trained (train = one byte per get_frequency() call)"})
     with open(os.path.join(HERE, "kat_vectors.json"), "w") as fh:
         json.dump(vecs, fh, indent=0)
     print("kat_vectors.json:", len(vecs), "vectors")

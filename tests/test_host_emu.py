@@ -382,3 +382,26 @@ def test_wide_decoder_quotient_estimate_and_its_fallback(emu):
         assert emu_encode(emu, [big, b"abc"], f, c)[0] == want
         outs, raw_len, consumed, status = emu_decode(emu, [want], [len(big)], f, c)
         assert int(status[0]) == 0 and outs[0] == big and int(consumed[0]) == len(want)
+
+
+def test_kernels_equal_the_golden_vectors(emu):
+    """Every committed golden vector (tests/golden/make_golden.py: an independent second reading of the
+    reference, incl. odd symbol widths and models trained before the call) through the kernels that would
+    code it on the device: tuned lane kernels for fresh byte models, generic kernels otherwise."""
+    import json
+    vecs = json.load(open(os.path.join(HERE, "golden", "kat_vectors.json")))
+    assert len(vecs) >= 130
+    for v in vecs:
+        s, f, c = v["params"]
+        data, want = bytes.fromhex(v["input"]), bytes.fromhex(v["compressed"])
+        nbytes = (len(data) * 8 // s) * s // 8
+        if s == 8 and "train" not in v:
+            assert emu_encode(emu, [data], f, c) == [want], v["name"]
+            outs, raw_len, consumed, status = emu_decode(emu, [want], [len(data)], f, c)
+        else:
+            freq = None
+            if "train" in v:
+                freq = o.trained_frequencies(list(bytes.fromhex(v["train"])), o.TREE, (s, f, c))
+            assert gen_encode(emu, [data], (s, f, c), freq=freq) == [want], v["name"]
+            outs, raw_len, consumed, status = gen_decode(emu, [want], [len(data)], (s, f, c), freq=freq)
+        assert int(status[0]) == 0 and outs[0] == data[:nbytes] and int(consumed[0]) == len(want), v["name"]

@@ -18,12 +18,19 @@ def test_kat_vectors_compress_and_roundtrip(kind):
         s, f, c = v["params"]
         data = bytes.fromhex(v["input"])
         want = bytes.fromhex(v["compressed"])
-        rc, out, ic, oc = o.compress(data, kind, (s, f, c))
+        train = list(bytes.fromhex(v["train"])) if "train" in v else None
+        if train is None:
+            rc, out, ic, oc = o.compress(data, kind, (s, f, c))
+        else:   # the caller trained the model first (src/model/mod.rs:23-25)
+            rc, out, ic, oc = o.compress_trained(data, train, kind, (s, f, c))
         assert rc == o.OK, v["name"]
         assert out == want, (v["name"], v["params"])
         assert oc == len(want)
         assert ic == len(data)
-        rc, dec, ic2, oc2 = o.decompress(out, kind, (s, f, c), out_cap=len(data) + 16)
+        if train is None:
+            rc, dec, ic2, oc2 = o.decompress(out, kind, (s, f, c), out_cap=len(data) + 16)
+        else:
+            rc, dec, ic2, oc2 = o.decompress_trained(out, train, kind, (s, f, c), out_cap=len(data) + 16)
         assert rc == o.OK
         assert ic2 == len(out), "decoder must consume exactly the compressed stream"
         nbits = (len(data) * 8 // s) * s  # trailing partial symbol is dropped
