@@ -411,8 +411,11 @@ def test_multi_device_context_shards_by_block_ranges():
     lens = np.full(n, L, dtype=np.uint64); lens[::7] = 0; lens[5::11] = 17      # ragged, some empty
     off = np.zeros(n + 1, dtype=np.uint64); np.cumsum(lens, out=off[1:])
     data = np.concatenate([raw[i * L:i * L + int(lens[i])] for i in range(n)])
-    for params in ((8, 14, 16), (8, 30, 32), (12, 22, 24)):
+    for params, trained in (((8, 14, 16), False), ((8, 30, 32), False), ((12, 22, 24), False), ((8, 14, 16), True)):
         model = rb.AdaptiveTreeModel(rb.Parameters(*params))
+        train = [int(x) for x in raw[:500]] if trained else None
+        if trained:
+            model.train(train)
         with rb.Context([0]) as one:
             ref_comp, ref_off, ref_st = one.encode_batch(data, off, model)
         with rb.Context(list(range(ng))) as many:
@@ -425,4 +428,5 @@ def test_multi_device_context_shards_by_block_ranges():
                 assert (rl == lens).all() and (back[: int(off[-1])] == data).all()
         for i in (0, 1, 2, 1500, 3000):
             b = data[int(off[i]):int(off[i + 1])]
-            assert comp[int(coff[i]):int(coff[i + 1])].tobytes() == o.compress(b, o.TREE, params)[1], (params, i)
+            want = o.compress_trained(b, train, o.TREE, params)[1] if trained else o.compress(b, o.TREE, params)[1]
+            assert comp[int(coff[i]):int(coff[i + 1])].tobytes() == want, (params, i)
