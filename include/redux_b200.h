@@ -137,6 +137,7 @@ int redux_decode_batch(redux_ctx_t *ctx, int model_kind, const redux_params_t *p
  * observable state of either model kind is its per-symbol frequency vector.  model_freq[symbol_count]
  * (symbol_count = 2^symbol_bits + 1, EOF last; every entry >= 1, sum <= freq_max, else
  * REDUX_INVALID_INPUT) is that vector; NULL = a fresh model.  Every block of the batch starts from it.
+ * Byte-symbol models with code_bits <= 32 run on the same tuned kernels as fresh models (same speed).
  * Otherwise identical to redux_encode_batch / redux_decode_batch. */
 int redux_encode_batch_ex(redux_ctx_t *ctx, int model_kind, const redux_params_t *params,
                           const uint32_t *model_freq,

@@ -159,6 +159,8 @@ struct Plan {
     bool aligned = false, full_table = false;   // see LanePlan
     // generic path (redux_generic_codec.cuh): symbol_bits != 8 or a pre-trained model
     bool generic = false; uint32_t s = 8, gen_threads = 0, gen_total = 0;
+    // byte symbols, code_bits <= 32, model trained before the call: the tuned lane kernels start from its tree
+    bool pretrained = false; uint32_t count0 = kNsym, eof_freq = 1;
     uint32_t *gen_tabs = nullptr; const uint32_t *gen_init = nullptr;
     bool warp = false;      // one stream per warp (latency mapping) instead of one per lane
     bool split = false;     // encode only: parallel model phase + one-warp coder chain (redux_split_encoder.cuh)
@@ -200,7 +202,21 @@ int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, P
         return fail(ctx, REDUX_UNSUPPORTED, "blocks longer than 2^32-16 bytes are not supported");
     pl->s = p->symbol_bits;
     pl->max_len = max_block_len;
-    pl->generic = p->symbol_bits != (uint32_t)kSymbolBits || ctx->model_freq != nullptr;
+    const bool huge = arith_class(p->freq_bits, p->code_bits) == kHuge;
+    pl->generic = p->symbol_bits != (uint32_t)kSymbolBits || (ctx->model_freq != nullptr && huge);
+    uint64_t total0 = ((uint64_t)1 << p->symbol_bits) + 1;
+    if (ctx->model_freq) {
+        // the observable state of a trained reference model: every symbol at least once, total <= freq_max
+        // (it starts at symbol_count and stops growing at freq_max, adaptive_tree.rs:84)
+        const uint64_t nsym = total0, fmax = ((uint64_t)1 << p->freq_bits) - 1;
+        total0 = 0;
+        for (uint64_t i = 0; i < nsym; ++i) {
+            if (ctx->model_freq[i] < 1) return fail(ctx, REDUX_INVALID_INPUT, "model frequency below 1");
+            total0 += ctx->model_freq[i];
+        }
+        if (total0 > fmax) return fail(ctx, REDUX_INVALID_INPUT, "model total exceeds freq_max");
+    }
+    pl->gen_total = (uint32_t)total0;
     if (pl->generic) {
         // worst case: every coded symbol (floor(8 len / s) data symbols + EOF) emits code_bits bits
         pl->f = p->freq_bits; pl->c = p->code_bits; pl->cls = kHuge; pl->tcap = 0; pl->wide_table = true;
@@ -209,7 +225,10 @@ int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, P
         pl->slot_stride = ((bound + 15) & ~(uint64_t)15) + 16;
         return REDUX_OK;
     }
-    const LanePlan lp = lane_plan(p->freq_bits, p->code_bits, max_block_len);
+    // (trained) tuned lane kernels: count_t = min(count0 + t, FMAX), full tree values in the table
+    pl->pretrained = ctx->model_freq != nullptr;
+    pl->count0 = (uint32_t)total0; pl->eof_freq = ctx->model_freq ? ctx->model_freq[kEof] : 1u;
+    const LanePlan lp = lane_plan(p->freq_bits, p->code_bits, max_block_len, pl->count0, pl->pretrained);
     pl->f = lp.f; pl->c = lp.c; pl->cls = lp.cls; pl->tcap = lp.tcap; pl->wide_table = lp.wide_table;
     pl->magic_len = lp.magic_len; pl->slot_stride = lp.slot_stride;
     pl->aligned = lp.aligned; pl->full_table = lp.full_table;
@@ -243,19 +262,10 @@ int get_magic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const Plan &p
 // sizes the per-thread Fenwick columns.  At most ~2 GB of columns; a thread codes several blocks in turn.
 int prepare_generic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const redux_params_t *p, uint64_t n_blocks, Plan *pl)
 {
-    if (!pl->generic) return REDUX_OK;
+    if (!pl->generic && !pl->pretrained) return REDUX_OK;
     const uint32_t nsym = (1u << p->symbol_bits) + 1;
-    const uint64_t fmax = ((uint64_t)1 << p->freq_bits) - 1;
-    uint64_t total = nsym;
     const uint32_t *d_freq = nullptr;
-    if (ctx->model_freq) {
-        total = 0;
-        for (uint32_t i = 0; i < nsym; ++i) {
-            if (ctx->model_freq[i] < 1) return fail(ctx, REDUX_INVALID_INPUT, "model frequency below 1");
-            total += ctx->model_freq[i];
-        }
-        // a reference model starts at symbol_count and stops growing at freq_max (adaptive_tree.rs:84)
-        if (total > fmax) return fail(ctx, REDUX_INVALID_INPUT, "model total exceeds freq_max");
+    if (ctx->model_freq) {                                   // validated by make_plan
         CU_TRY(ctx, d->gen_freq.reserve(nsym * sizeof(uint32_t)));
         CU_TRY(ctx, cudaMemcpyAsync(d->gen_freq.p, ctx->model_freq, nsym * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
         d_freq = (const uint32_t *)d->gen_freq.p;
@@ -264,6 +274,11 @@ int prepare_generic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const r
     build_tree_kernel<<<(nsym + 1 + 255) / 256, 256, 0, stream>>>(d_freq, nsym, (uint32_t *)d->gen_init.p);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
+    pl->gen_init = (const uint32_t *)d->gen_init.p;
+    if (!pl->generic) {                                      // tuned lane kernels: only the start tree is needed
+        CU_TRY(ctx, cudaStreamSynchronize(stream));
+        return REDUX_OK;
+    }
     const uint64_t col_bytes = (uint64_t)(nsym + 1) * sizeof(uint32_t);
     uint64_t threads = std::min<uint64_t>((n_blocks + kGenericThreads - 1) / kGenericThreads * kGenericThreads,
                                           (uint64_t)148 * 16 * kGenericThreads);
@@ -272,9 +287,17 @@ int prepare_generic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const r
     CU_TRY(ctx, d->gen_tabs.reserve(threads * col_bytes));
     // the start tree must be complete before kernels on other streams read it; the upload buffer is reused
     CU_TRY(ctx, cudaStreamSynchronize(stream));
-    pl->gen_threads = (uint32_t)threads; pl->gen_total = (uint32_t)total;
-    pl->gen_tabs = (uint32_t *)d->gen_tabs.p; pl->gen_init = (const uint32_t *)d->gen_init.p;
+    pl->gen_threads = (uint32_t)threads;
+    pl->gen_tabs = (uint32_t *)d->gen_tabs.p;
     return REDUX_OK;
+}
+
+// Reciprocal table as the kernels index it: entry t <-> count0 + t (the table itself starts at count 257).
+const void *lane_magic(const Plan &pl, const void *magic)
+{
+    if (!magic || !pl.pretrained) return magic;
+    const size_t esz = pl.cls == kNarrow ? sizeof(Magic32) : sizeof(Magic64);
+    return (const uint8_t *)magic + (size_t)(pl.count0 - kNsym) * esz;
 }
 
 GenericJob generic_job(const Plan &pl)
@@ -611,8 +634,9 @@ int encode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     job.in = d_in; job.in_off = d_in_off; job.n_blocks = n_blocks;
     job.slots = slots; job.slot_stride = pl.slot_stride;
     job.sizes = sizes; job.status = d_status;
-    job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    job.magic = lane_magic(pl, magic); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
     job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
+    job.init_tree = pl.pretrained ? pl.gen_init : nullptr; job.count0 = pl.count0; job.eof_freq = pl.eof_freq;
     const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
     const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2) + kTabPadBytes;
     {
@@ -660,8 +684,9 @@ int decode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     LaneDecJob job;
     job.comp = d_comp; job.comp_off = d_comp_off; job.n_blocks = n_blocks;
     job.raw = d_raw; job.raw_off = d_raw_off; job.raw_len = d_raw_lens; job.consumed = d_consumed;
-    job.status = d_status; job.magic = magic; job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    job.status = d_status; job.magic = lane_magic(pl, magic); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
     job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
+    job.init_tree = pl.pretrained ? pl.gen_init : nullptr; job.count0 = pl.count0; job.eof_freq = pl.eof_freq;
     const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
     const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2) + kTabPadBytes;
     {
@@ -695,8 +720,8 @@ extern "C" int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *str
     if ((rc = check_kind(ctx, model_kind))) return rc;
     Plan pl;
     if ((rc = make_plan(ctx, params, max_block_len, &pl))) return rc;
-    pl.warp = !pl.generic && choose_warp(ctx, n_blocks);
-    pl.split = !pl.generic && choose_split(ctx, n_blocks, pl.cls, max_block_len);
+    pl.warp = !pl.generic && !pl.pretrained && choose_warp(ctx, n_blocks);
+    pl.split = !pl.generic && !pl.pretrained && choose_split(ctx, n_blocks, pl.cls, max_block_len);
     DeviceState *d = find_dev(ctx, device);
     if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
     if (!d_in_offsets || !d_out_offsets || !d_status || (!d_out && out_capacity))
@@ -729,7 +754,7 @@ extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *str
     if ((rc = check_kind(ctx, model_kind))) return rc;
     Plan pl;
     if ((rc = make_plan(ctx, params, max_block_len, &pl))) return rc;
-    pl.warp = !pl.generic && choose_warp(ctx, n_blocks) && !(ctx->sched == REDUX_SCHED_AUTO && pl.cls == kNarrow);
+    pl.warp = !pl.generic && !pl.pretrained && choose_warp(ctx, n_blocks) && !(ctx->sched == REDUX_SCHED_AUTO && pl.cls == kNarrow);
     DeviceState *d = find_dev(ctx, device);
     if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
     if (n_blocks == 0) return REDUX_OK;
@@ -920,8 +945,8 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     Plan pl;
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
-    pl.warp = !pl.generic && choose_warp(ctx, sh.count);
-    pl.split = !pl.generic && choose_split(ctx, sh.count, pl.cls, max_len);
+    pl.warp = !pl.generic && !pl.pretrained && choose_warp(ctx, sh.count);
+    pl.split = !pl.generic && !pl.pretrained && choose_split(ctx, sh.count, pl.cls, max_len);
     // chunks of the generic path would share the Fenwick columns (and split chunks the range workspace): one chunk
     res->chunks = (pl.generic || pl.split) ? std::vector<Shard>{{0, sh.count}} : make_chunks(sh.count, +1);
     const size_t nc = res->chunks.size();
@@ -1103,7 +1128,7 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
     // small batches: the cooperating warp decodes 64-bit-product classes faster, a lone lane the narrow class
-    pl.warp = !pl.generic && choose_warp(ctx, sh.count) && !(ctx->sched == REDUX_SCHED_AUTO && pl.cls == kNarrow);
+    pl.warp = !pl.generic && !pl.pretrained && choose_warp(ctx, sh.count) && !(ctx->sched == REDUX_SCHED_AUTO && pl.cls == kNarrow);
     const std::vector<Shard> chunks = pl.generic ? std::vector<Shard>{{0, sh.count}} : make_chunks(sh.count, -1);
     const size_t nc = chunks.size();
     CU_TRY(ctx, d->st_in.reserve(cbytes + 32));

@@ -161,19 +161,23 @@ struct LanePlan {
     bool aligned;     // c <= 32 (32-bit coder state): the tuned kernels of redux_lane_al.cuh
     bool full_table;  // table entries can hold the reference's tree values (lowbit + increments)
 };
-RDX_HD LanePlan lane_plan(uint32_t f, uint32_t c, uint64_t max_block_len) {
+// count0 = total frequency of the start model: symbol_count for a fresh one, larger for a model the caller
+// trained before the call (then the table must hold full tree values: pretrained = true).
+RDX_HD LanePlan lane_plan(uint32_t f, uint32_t c, uint64_t max_block_len, uint32_t count0 = kNsym,
+                          bool pretrained = false) {
     LanePlan pl;
     pl.f = f; pl.c = c;
     pl.cls = arith_class(f, c);
     const uint64_t fmax = ((uint64_t)1 << f) - 1;
-    pl.tcap = (uint32_t)(fmax - kNsym);                        // f <= 31 -> fits
+    pl.tcap = (uint32_t)(fmax - count0);                       // f <= 31 -> fits
     const uint64_t updates = max_block_len < pl.tcap ? max_block_len : pl.tcap;
-    pl.wide_table = updates > 65536;                           // u16 increments suffice otherwise
-    pl.magic_len = (uint32_t)updates + 2;                      // positions 0..updates, +1 read-ahead
+    // u16 entries suffice while increments (fresh) / cumulative values (trained) fit
+    pl.wide_table = pretrained ? (uint64_t)count0 + updates > 65535 : updates > 65536;
+    pl.magic_len = (uint32_t)(count0 - kNsym + updates) + 2;   // counts 257 .. count0 + updates, +1 read-ahead
     const uint64_t bound = ((max_block_len + 1) * (uint64_t)c + 7) / 8;
     pl.slot_stride = ((bound + 15) & ~(uint64_t)15) + 16;
     pl.aligned = pl.cls != kHuge;
-    pl.full_table = pl.wide_table || updates + 256 <= 65535;   // cum(i) <= 256 + updates must fit u16
+    pl.full_table = pretrained || pl.wide_table || updates + 256 <= 65535;   // cum(i) <= 256 + updates must fit u16
     return pl;
 }
 

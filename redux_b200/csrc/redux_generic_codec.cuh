@@ -1,7 +1,7 @@
-// redux_generic_codec.cuh -- the whole Parameters space and pre-trained models.
+// redux_generic_codec.cuh -- the rest of the Parameters space.
 //
-// The tuned kernels (redux_lane_al.cuh) assume byte symbols and a fresh model.  Everything else the
-// reference accepts runs here, still one stream per lane and still bit-exact:
+// The tuned kernels (redux_lane_al.cuh) cover byte symbols with code_bits <= 32, fresh or pre-trained.
+// Everything else the reference accepts runs here, still one stream per lane and still bit-exact:
 //   * any symbol_bits 1..16 (Parameters::new allows any width, src/model/mod.rs:63-81; the reference's
 //     model tests run 4 and 12, src/model/tests.rs:95-251).  Symbols are read MSB-first across byte
 //     boundaries exactly like BitReader::read_bits (src/bitio/mod.rs:78-120): a trailing partial symbol
@@ -10,7 +10,8 @@
 //     a byte are lost -- both quirks of the reference are reproduced, not repaired;
 //   * any code_bits (64-bit coder state, plain 64-bit division: products stay below 2^64 because
 //     code_bits + freq_bits <= 64, src/model/mod.rs:64);
-//   * a model that was TRAINED before compress()/decompress() received it: the reference takes a
+//   * with those, a model that was TRAINED before compress()/decompress() received it (trained byte models
+//     with code_bits <= 32 run on the tuned kernels): the reference takes a
 //     Box<Model> (src/lib.rs:102) whose get_frequency() has possibly been called already
 //     (src/model/mod.rs:23-25); its state is exactly the per-symbol frequency vector, handed over here
 //     as the Fenwick tree built from it.

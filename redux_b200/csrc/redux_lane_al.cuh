@@ -63,10 +63,19 @@ struct LaneTable2 : LaneTable<TW> {
     using B = LaneTable<TW>;
     using B::t;
 
-    __device__ __forceinline__ void reset() {
+    // init_tree != NULL: start from a model the caller trained (FULL tables only); tree[0..255] as u32
+    __device__ __forceinline__ void reset(const uint32_t *init_tree = nullptr) {
         uint32_t *w = reinterpret_cast<uint32_t *>(t);
         constexpr int kWords = kTabNodes * (int)sizeof(TW) / 4;
-        if (!FULL) {
+        if (FULL && init_tree) {
+            if (sizeof(TW) == 2) {
+#pragma unroll 4
+                for (int m = 0; m < kWords; ++m) w[m * 32] = __ldg(init_tree + 2 * m) | (__ldg(init_tree + 2 * m + 1) << 16);
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < kWords; ++i) w[i * 32] = __ldg(init_tree + i);
+            }
+        } else if (!FULL) {
 #pragma unroll 8
             for (int i = 0; i < kWords; ++i) w[i * 32] = 0;
         } else if (sizeof(TW) == 2) {
@@ -80,9 +89,10 @@ struct LaneTable2 : LaneTable<TW> {
     }
 
     // (cum(s), cum(s+1)) of adaptive_tree.rs:63-80 and, when UPDATE, update(s+1) of :83-92, sharing the
-    // node addresses.  `updates` = number of updates so far (the unstored node 256 is 256 + updates).
+    // node addresses.  `cum256` = cum(256) = total - frequency of EOF (the unstored node 256; for a fresh model
+    // 256 + the number of updates so far); with increments-only tables (!FULL) the caller passes it minus 256.
     template <bool UPDATE>
-    __device__ __forceinline__ void query(uint32_t s, uint32_t updates, uint32_t &cl, uint32_t &ch) {
+    __device__ __forceinline__ void query(uint32_t s, uint32_t cum256, uint32_t &cl, uint32_t &ch) {
         const uint32_t S = s << 5;
         const uint32_t bothmask = s & (s + 1);                 // set bits above the lowest zero bit
         const uint32_t q = ~s & 255u;                          // clear bits of s
@@ -117,7 +127,7 @@ struct LaneTable2 : LaneTable<TW> {
                 both += (bothmask & (1u << b)) ? v[b] : 0u;
             }
         }
-        const uint32_t top = odd ? (last ? updates + (FULL ? 256u : 0u) : xn) : xo;
+        const uint32_t top = odd ? (last ? cum256 : xn) : xo;
         cl = total + (FULL ? 0u : s);
         ch = top + both + (FULL ? 0u : s + 1u);
         if (UPDATE) {
@@ -166,7 +176,7 @@ struct LaneTable2 : LaneTable<TW> {
             t[B::node_index(i)] = (TW)sum;
         }
     }
-    __device__ __forceinline__ void query_frozen(uint32_t s, uint32_t count, uint32_t &cl, uint32_t &ch) const {
+    __device__ __forceinline__ void query_frozen(uint32_t s, uint32_t cum256, uint32_t &cl, uint32_t &ch) const {
         uint32_t lo, hi;
         if (sizeof(TW) == 2) {
             const uint32_t *w = reinterpret_cast<const uint32_t *>(t);
@@ -179,7 +189,7 @@ struct LaneTable2 : LaneTable<TW> {
             hi = t[((s + 1) & 255u) << 5];
         }
         cl = lo + (FULL ? 0u : s);
-        ch = (s == 255u) ? count - 1 : hi + (FULL ? 0u : s + 1u);
+        ch = (s == 255u) ? cum256 : hi + (FULL ? 0u : s + 1u);
     }
 };
 
@@ -318,11 +328,12 @@ encode_lane_al_kernel(const LaneEncJob job)
 
     LaneTable2<TW, FULL> tab;
     tab.init(smem_u4, warp, lane);
-    tab.reset();
+    tab.reset(job.init_tree);
 
     const uint64_t off = job.in_off[blk];
     const uint32_t len = (uint32_t)(job.in_off[blk + 1] - off);
     const uint32_t c = job.c, sh = 32 - c, one = job.one;
+    const uint32_t count0 = job.count0, eof_freq = job.eof_freq;   // 257 and 1 for a fresh model
     const M *magic = reinterpret_cast<const M *>(job.magic);
     const uint32_t tcap = job.tcap;
 
@@ -342,29 +353,31 @@ encode_lane_al_kernel(const LaneEncJob job)
         gn = C::ldm(magic + t + 1);
         const uint32_t sym = src.next();
         uint32_t cl, ch;
-        tab.template query<true>(sym, t, cl, ch);
-        encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, kNsym + t, g, sh, one);
+        // cum(256) = total - freq(EOF); increments-only tables (fresh models only) keep the 256 implicit
+        tab.template query<true>(sym, count0 + t - eof_freq - (FULL ? 0u : 256u), cl, ch);
+        encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, count0 + t, g, sh, one);
     }
     // frozen phase (adaptive_tree.rs:84): total == FMAX, table and reciprocal are constant
     const M gf = gn;                                       // = magic[n_adapt]
-    const uint32_t countf = kNsym + n_adapt;
+    const uint32_t countf = count0 + n_adapt;
+    const uint32_t cum256f = countf - eof_freq;
     if (t < len) {
         tab.freeze_to_cumulative();
         // the lookup does not depend on the coder state: look symbol t+1 up before coding
         // symbol t, so the shared-memory latency overlaps the range update
         uint32_t cl, ch;
-        tab.query_frozen(src.next(), countf, cl, ch);
+        tab.query_frozen(src.next(), cum256f, cl, ch);
         for (; t + 1 < len; ++t) {
             const uint32_t cl_cur = cl, ch_cur = ch;
-            tab.query_frozen(src.next(), countf, cl, ch);
+            tab.query_frozen(src.next(), cum256f, cl, ch);
             encode_step_al<CLS, C32>(L, H, pend, sink, cl_cur, ch_cur, countf, gf, sh, one);
         }
         encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, countf, gf, sh, one);
         ++t;
     }
-    // EOF symbol: cum(256) = total - 1, then the tail of src/codec.rs:91-99: the remaining `extra` MSBs of
+    // EOF symbol: [cum(256), total), then the tail of src/codec.rs:91-99: the remaining `extra` MSBs of
     // low, the first of them carrying the pending run, then flush
-    const uint32_t shifts = encode_step_al<CLS, C32>(L, H, pend, sink, countf - 1, countf, countf, gf, sh, one);
+    const uint32_t shifts = encode_step_al<CLS, C32>(L, H, pend, sink, cum256f, countf, countf, gf, sh, one);
     const uint32_t extra = c - shifts;
     sink.put_code(top_bits(L, extra), extra, pend, 0);
     job.sizes[blk] = sink.finish();
@@ -419,6 +432,7 @@ struct LaneDecoderAl {
     ByteSink out;
     uint32_t L, H, V;    // left-aligned low / high (src/codec.rs:11-24) and the code-value window
     uint32_t sh, one, t, left;   // one == 1 << sh, opaque to the compiler (keeps q * one + L an IMAD)
+    uint32_t count0, eof_freq;   // start total / frequency of EOF (257 / 1 for a fresh model)
     int32_t st;          // 0 running, -1 EOF symbol decoded (success), >0 error code
 
     // Decodes symbols while t < t_end.  ADAPT: the model still learns (count = 257 + t, one reciprocal per
@@ -434,14 +448,14 @@ struct LaneDecoderAl {
             top_a = tab.t[128 << 5]; top_b = tab.t[64 << 5]; top_c = tab.t[192 << 5];
         }
         while (t < t_end) {
-            const uint32_t count = ADAPT ? kNsym + t : count_frozen;
+            const uint32_t count = ADAPT ? count0 + t : count_frozen;
             const M g = gn;
             if (ADAPT && !PEEK) gn = C::ldm(magic + t + 1);
             // src/codec.rs:129-131 without the division: find i with cum(i)*range <= X < cum(i+1)*range,
             // X = (value-low+1)*count - 1
             const uint32_t rm1 = (H - L) >> sh;
             const P X = C::mulr(count, (V - L) >> sh) - 1;
-            P plo = 0, phi = C::mulr(count - 1, rm1);             // node 256 = cum(256) = count - 1
+            P plo = 0, phi = C::mulr(count - eof_freq, rm1);      // node 256 = cum(256) = count - freq(EOF)
             uint32_t I = 0;                                       // i * 32
             const bool is_eof = X >= phi;
             if (CLS == kNarrow) {
@@ -492,7 +506,7 @@ struct LaneDecoderAl {
                 const P pv = C::mulr(v, rm1);                     // v * range
                 if (pv > X) v -= 1u;                              // estimate one too high
                 else if (X - pv > (P)rm1) v += 1u;                // one too low (remainder >= range)
-                uint32_t lo = 0, hi = count - 1;                  // cum(i) <= v < hi tracked in the value domain
+                uint32_t lo = 0, hi = count - eof_freq;           // cum(i) <= v < hi tracked in the value domain
 #pragma unroll
                 for (int m = 128; m >= 2; m >>= 2) {
                     const int h = m >> 1;
@@ -554,7 +568,7 @@ decode_lane_al_kernel(const LaneDecJob job)
 
     D d;
     d.tab.init(smem_u4, warp, lane);
-    d.tab.reset();
+    d.tab.reset(job.init_tree);
 
     const uint64_t coff = job.comp_off[blk];
     const uint64_t clen = job.comp_off[blk + 1] - coff;
@@ -567,7 +581,7 @@ decode_lane_al_kernel(const LaneDecJob job)
     const uint32_t c = job.c;
     const uint32_t cap = cap64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)cap64;
     const uint32_t total_bits = (uint32_t)clen * 8;
-    d.sh = 32 - c; d.one = job.one;
+    d.sh = 32 - c; d.one = job.one; d.count0 = job.count0; d.eof_freq = job.eof_freq;
     d.out.init(job.raw + roff);
     d.st = 0; d.t = 0;
     d.L = 0; d.H = 0xFFFFFFFFu; d.V = 0; d.left = 0;
@@ -589,8 +603,8 @@ decode_lane_al_kernel(const LaneDecJob job)
     }
     if (d.st == 0) {
         const M gf = D::C::ldm(magic + tcap);
-        d.template run<false, false>(cap, magic, kNsym + tcap, gf);
-        if (d.st == 0) d.template run<false, true>(d.t + 1, magic, kNsym + tcap, gf);
+        d.template run<false, false>(cap, magic, d.count0 + tcap, gf);
+        if (d.st == 0) d.template run<false, true>(d.t + 1, magic, d.count0 + tcap, gf);
     }
     d.out.finish();
     job.raw_len[blk] = d.t;

@@ -48,6 +48,10 @@ struct LaneEncJob {
     uint32_t f, c;
     uint32_t tcap;              // FMAX - NSYM: number of model updates before the freeze
     uint32_t one;               // 1 << (32 - c) for c <= 32 (redux_lane_al.cuh), else 0
+    // pre-trained start state (tuned kernels only): NULL / 257 / 1 for a fresh model
+    const uint32_t *init_tree;  // tree[0..255] of the start model (adaptive_tree.rs layout), or NULL
+    uint32_t count0;            // its total frequency; `magic` entry t <-> count0 + t, tcap = FMAX - count0
+    uint32_t eof_freq;          // frequency of the EOF symbol: cum(256) = total - eof_freq
 };
 
 struct LaneDecJob {
@@ -63,6 +67,8 @@ struct LaneDecJob {
     uint32_t f, c;
     uint32_t tcap;
     uint32_t one;               // as in LaneEncJob
+    const uint32_t *init_tree;  // as in LaneEncJob
+    uint32_t count0, eof_freq;
 };
 
 // ------------------------------------------------------------------ arithmetic class traits

@@ -1,4 +1,4 @@
-"""Generic path (redux_generic_codec.cuh): symbol widths other than 8 and pre-trained models.
+"""Generic path (redux_generic_codec.cuh): symbol widths other than 8, pre-trained models with code_bits > 32.
 8,192 mixed-entropy blocks of 16 KiB; kernel times from the library's own CUDA-event brackets."""
 import json, os, sys
 import numpy as np
@@ -13,6 +13,7 @@ off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
 ctx = rb.Context([0])
 res = {}
 cases = [("s=4 (4,10,16)", (4, 10, 16), None), ("s=12 (12,22,24)", (12, 22, 24), None), ("s=16 (16,18,20)", (16, 18, 20), None),
+         ("s=8 pre-trained, code_bits 34: generic kernels (8,30,34)", (8, 30, 34), [int(x) for x in raw[:4000]])]
 for name, params, train in cases:
     model = rb.AdaptiveTreeModel(rb.Parameters(*params))
     if train: model.train(train)

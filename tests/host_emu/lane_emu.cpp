@@ -59,11 +59,36 @@ extern "C" uint64_t emu_slot_stride(uint32_t f, uint32_t c, uint64_t max_block_l
 
 // force_wide_table: -1 = as the front end would choose, 0 = u16 entries, 1 = u32 entries; +2 = force the
 // generic kernels (redux_lane_codec.cuh) where the tuned ones (redux_lane_al.cuh) would be chosen
-extern "C" int emu_encode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, int force_wide_table,
-                               const uint8_t *in, const uint64_t *in_off, uint64_t n_blocks,
-                               uint8_t *slots, uint32_t *sizes, int32_t *status)
+namespace {
+// start state of a trained byte model for the tuned lane kernels: tree[0..257], total, EOF frequency
+struct LaneStart { std::vector<uint32_t> tree; uint32_t count0 = kNsym, eof_freq = 1; bool on = false; };
+LaneStart lane_start(const uint32_t *freq)
 {
-    LanePlan pl = lane_plan(f, c, max_block_len);
+    LaneStart st;
+    if (!freq) return st;
+    st.on = true;
+    st.tree.assign(kNsym + 1, 0);
+    blockDim.x = 256; gridDim.x = 2;
+    for (uint32_t b = 0; b < 2; ++b)
+        for (uint32_t t = 0; t < 256; ++t) { blockIdx.x = b; threadIdx.x = t; build_tree_kernel(freq, kNsym, st.tree.data()); }
+    st.count0 = 0;
+    for (uint32_t i = 0; i < kNsym; ++i) st.count0 += freq[i];
+    st.eof_freq = freq[kEof];
+    return st;
+}
+const void *shift_magic(const LanePlan &pl, const std::vector<uint8_t> &magic, uint32_t count0)
+{
+    if (magic.empty()) return nullptr;
+    return magic.data() + (size_t)(count0 - kNsym) * (pl.cls == kNarrow ? sizeof(Magic32) : sizeof(Magic64));
+}
+}  // namespace
+
+extern "C" int emu_encode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len, int force_wide_table, const uint32_t *freq,
+                                  const uint8_t *in, const uint64_t *in_off, uint64_t n_blocks,
+                                  uint8_t *slots, uint32_t *sizes, int32_t *status)
+{
+    const LaneStart st0 = lane_start(freq);
+    LanePlan pl = lane_plan(f, c, max_block_len, st0.count0, st0.on);
     const bool legacy = force_wide_table >= 2;            // 2/3: the generic kernels of redux_lane_codec.cuh
     if (force_wide_table >= 2) force_wide_table -= 2;
     if (force_wide_table >= 0) { pl.wide_table = force_wide_table != 0; if (pl.wide_table) pl.full_table = true; }
@@ -71,8 +96,9 @@ extern "C" int emu_encode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, i
     LaneEncJob job;
     job.in = in; job.in_off = in_off; job.n_blocks = n_blocks;
     job.slots = slots; job.slot_stride = pl.slot_stride; job.sizes = sizes; job.status = status;
-    job.magic = magic.data(); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    job.magic = shift_magic(pl, magic, st0.count0); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
     job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
+    job.init_tree = st0.on ? st0.tree.data() : nullptr; job.count0 = st0.count0; job.eof_freq = st0.eof_freq;
 #define RUN(TW) \
     (pl.cls == kNarrow ? run_grid(encode_lane_kernel<TW, kNarrow>, job, n_blocks) : \
      pl.cls == kWide   ? run_grid(encode_lane_kernel<TW, kWide>, job, n_blocks)   : \
@@ -91,12 +117,20 @@ extern "C" int emu_encode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, i
     return 0;
 }
 
-extern "C" int emu_decode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, int force_wide_table,
-                               const uint8_t *comp, const uint64_t *comp_off, uint64_t n_blocks,
-                               uint8_t *raw, const uint64_t *raw_off, uint64_t *raw_len,
-                               uint64_t *consumed, int32_t *status)
+extern "C" int emu_encode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, int force_wide_table,
+                               const uint8_t *in, const uint64_t *in_off, uint64_t n_blocks,
+                               uint8_t *slots, uint32_t *sizes, int32_t *status)
 {
-    LanePlan pl = lane_plan(f, c, max_block_len);
+    return emu_encode_lane_ex(f, c, max_block_len, force_wide_table, nullptr, in, in_off, n_blocks, slots, sizes, status);
+}
+
+extern "C" int emu_decode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len, int force_wide_table, const uint32_t *freq,
+                                  const uint8_t *comp, const uint64_t *comp_off, uint64_t n_blocks,
+                                  uint8_t *raw, const uint64_t *raw_off, uint64_t *raw_len,
+                                  uint64_t *consumed, int32_t *status)
+{
+    const LaneStart st0 = lane_start(freq);
+    LanePlan pl = lane_plan(f, c, max_block_len, st0.count0, st0.on);
     const bool legacy = force_wide_table >= 2;            // 2/3: the generic kernels of redux_lane_codec.cuh
     if (force_wide_table >= 2) force_wide_table -= 2;
     if (force_wide_table >= 0) { pl.wide_table = force_wide_table != 0; if (pl.wide_table) pl.full_table = true; }
@@ -104,8 +138,9 @@ extern "C" int emu_decode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, i
     LaneDecJob job;
     job.comp = comp; job.comp_off = comp_off; job.n_blocks = n_blocks;
     job.raw = raw; job.raw_off = raw_off; job.raw_len = raw_len; job.consumed = consumed;
-    job.status = status; job.magic = magic.data(); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
+    job.status = status; job.magic = shift_magic(pl, magic, st0.count0); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
     job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
+    job.init_tree = st0.on ? st0.tree.data() : nullptr; job.count0 = st0.count0; job.eof_freq = st0.eof_freq;
 #define RUN(TW) \
     (pl.cls == kNarrow ? run_grid(decode_lane_kernel<TW, kNarrow>, job, n_blocks) : \
      pl.cls == kWide   ? run_grid(decode_lane_kernel<TW, kWide>, job, n_blocks)   : \
@@ -122,6 +157,15 @@ extern "C" int emu_decode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, i
 #undef RUN
 #undef RUN_AL
     return 0;
+}
+
+extern "C" int emu_decode_lane(uint32_t f, uint32_t c, uint64_t max_block_len, int force_wide_table,
+                               const uint8_t *comp, const uint64_t *comp_off, uint64_t n_blocks,
+                               uint8_t *raw, const uint64_t *raw_off, uint64_t *raw_len,
+                               uint64_t *consumed, int32_t *status)
+{
+    return emu_decode_lane_ex(f, c, max_block_len, force_wide_table, nullptr, comp, comp_off, n_blocks, raw, raw_off,
+                              raw_len, consumed, status);
 }
 
 // One coder step of the tuned kernels on an arbitrary (low, high) state, for the closed-form-vs-loop test.

@@ -41,6 +41,8 @@ def emu():
     L.emu_slot_stride.restype = u64
     L.emu_encode_lane.argtypes = [u32, u32, u64, i32, vp, vp, u64, vp, vp, vp]
     L.emu_decode_lane.argtypes = [u32, u32, u64, i32, vp, vp, u64, vp, vp, vp, vp, vp]
+    L.emu_encode_lane_ex.argtypes = [u32, u32, u64, i32, vp, vp, vp, u64, vp, vp, vp]
+    L.emu_decode_lane_ex.argtypes = [u32, u32, u64, i32, vp, vp, vp, u64, vp, vp, vp, vp, vp]
     L.emu_encode_generic.argtypes = [u32, u32, u32, vp, u32, vp, vp, u64, vp, u64, vp, vp]
     L.emu_decode_generic.argtypes = [u32, u32, u32, vp, u32, vp, vp, u64, vp, vp, vp, vp, vp]
     return L
@@ -56,7 +58,7 @@ def concat(blocks):
     return data, off
 
 
-def emu_encode(emu, blocks, f, c, wide=-1):
+def emu_encode(emu, blocks, f, c, wide=-1, freq=None):
     data, off = concat(blocks)
     n = len(blocks)
     max_len = max((len(b) for b in blocks), default=0)
@@ -66,13 +68,14 @@ def emu_encode(emu, blocks, f, c, wide=-1):
     base = (-slots.ctypes.data) % 16
     sizes = np.zeros(n, dtype=np.uint32)
     status = np.full(n, -1, dtype=np.int32)
-    emu.emu_encode_lane(f, c, max_len, wide, data.ctypes.data, off.ctypes.data, n,
-                        slots.ctypes.data + base, sizes.ctypes.data, status.ctypes.data)
+    fq = None if freq is None else np.ascontiguousarray(freq, dtype=np.uint32)
+    emu.emu_encode_lane_ex(f, c, max_len, wide, None if fq is None else fq.ctypes.data, data.ctypes.data,
+                           off.ctypes.data, n, slots.ctypes.data + base, sizes.ctypes.data, status.ctypes.data)
     assert (status == 0).all()
     return [slots[base + i * stride: base + i * stride + int(sizes[i])].tobytes() for i in range(n)]
 
 
-def emu_decode(emu, streams, caps, f, c, wide=-1):
+def emu_decode(emu, streams, caps, f, c, wide=-1, freq=None):
     comp, coff = concat(streams)
     n = len(streams)
     roff = np.zeros(n + 1, dtype=np.uint64)
@@ -81,9 +84,10 @@ def emu_decode(emu, streams, caps, f, c, wide=-1):
     raw_len = np.zeros(n, dtype=np.uint64)
     consumed = np.zeros(n, dtype=np.uint64)
     status = np.full(n, -1, dtype=np.int32)
-    emu.emu_decode_lane(f, c, max(caps, default=0), wide, comp.ctypes.data, coff.ctypes.data, n,
-                        raw.ctypes.data, roff.ctypes.data, raw_len.ctypes.data, consumed.ctypes.data,
-                        status.ctypes.data)
+    fq = None if freq is None else np.ascontiguousarray(freq, dtype=np.uint32)
+    emu.emu_decode_lane_ex(f, c, max(caps, default=0), wide, None if fq is None else fq.ctypes.data, comp.ctypes.data,
+                           coff.ctypes.data, n, raw.ctypes.data, roff.ctypes.data, raw_len.ctypes.data,
+                           consumed.ctypes.data, status.ctypes.data)
     outs = [raw[int(roff[i]): int(roff[i]) + int(raw_len[i])].tobytes() for i in range(n)]
     return outs, raw_len, consumed, status
 
@@ -395,9 +399,12 @@ def test_kernels_equal_the_golden_vectors(emu):
         s, f, c = v["params"]
         data, want = bytes.fromhex(v["input"]), bytes.fromhex(v["compressed"])
         nbytes = (len(data) * 8 // s) * s // 8
-        if s == 8 and "train" not in v:
-            assert emu_encode(emu, [data], f, c) == [want], v["name"]
-            outs, raw_len, consumed, status = emu_decode(emu, [want], [len(data)], f, c)
+        if s == 8 and (c <= 32 or "train" not in v):
+            freq = None
+            if "train" in v:     # trained byte model: the tuned lane kernels start from its tree
+                freq = o.trained_frequencies(list(bytes.fromhex(v["train"])), o.TREE, (s, f, c))
+            assert emu_encode(emu, [data], f, c, freq=freq) == [want], v["name"]
+            outs, raw_len, consumed, status = emu_decode(emu, [want], [len(data)], f, c, freq=freq)
         else:
             freq = None
             if "train" in v:
@@ -405,3 +412,35 @@ def test_kernels_equal_the_golden_vectors(emu):
             assert gen_encode(emu, [data], (s, f, c), freq=freq) == [want], v["name"]
             outs, raw_len, consumed, status = gen_decode(emu, [want], [len(data)], (s, f, c), freq=freq)
         assert int(status[0]) == 0 and outs[0] == data[:nbytes] and int(consumed[0]) == len(want), v["name"]
+
+
+@pytest.mark.parametrize("f,c", [(10, 12), (14, 16), (16, 18), (22, 24), (30, 32)])
+def test_lane_kernels_from_a_trained_model(emu, f, c):
+    """Byte symbols, code_bits <= 32, model trained before the call: the tuned lane kernels start from the
+    trained tree (count_t = min(count0 + t, FMAX), cum(256) = total - freq(EOF)).  Training sets include the
+    EOF symbol itself, a model trained all the way to the freeze, and totals that need u32 table entries."""
+    rng = np.random.default_rng(100 * f + c)
+    fmax = (1 << f) - 1
+    trainings = [
+        [int(x) for x in rng.integers(0, 40, 300)],
+        [256] * 5 + [int(x) for x in rng.integers(0, 257, 200)],            # EOF trained: freq(EOF) = 6
+        [int(x) for x in rng.integers(60, 70, min(fmax, 70000))],           # to the freeze (small f) / beyond u16 (large f)
+    ]
+    blocks = make_blocks(rng, 14, 2500) + [bytes([255] * 900), bytes(rng.integers(60, 70, 3000, dtype=np.uint8))]
+    for train in trainings:
+        freq = o.trained_frequencies(train, o.TREE, (8, f, c))
+        want = []
+        for b in blocks:
+            rc, out, ic, oc = o.compress_trained(b, train, o.LINEAR, (8, f, c))
+            assert rc == o.OK
+            want.append(out)
+        assert emu_encode(emu, blocks, f, c, freq=freq) == want, (f, c, len(train))
+        outs, raw_len, consumed, status = emu_decode(emu, want, [len(b) + 2 for b in blocks], f, c, freq=freq)
+        assert (status == 0).all() and outs == blocks
+        assert [int(x) for x in consumed] == [len(w) for w in want]
+        # truncated streams keep the reference's Eof behaviour
+        cut = [w[:-1] for w in want]
+        outs, raw_len, consumed, status = emu_decode(emu, cut, [len(b) + 2 for b in blocks], f, c, freq=freq)
+        for i, sgm in enumerate(cut):
+            rc, out, ic, oc = o.decompress_trained(sgm, train, o.TREE, (8, f, c), out_cap=len(blocks[i]) + 2)
+            assert (int(status[i]), outs[i], int(consumed[i])) == (rc, out, ic), (i, f, c)
