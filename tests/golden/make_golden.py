@@ -181,9 +181,65 @@ def make_kat():
             vecs.append({"name": "trained%d-%s-%d" % (ntrain, kind, n), "params": [s, f, c], "input": data.hex(),
                          "train": bytes(train).hex(), "compressed": coder.encode(data).hex(),
                          "source": "PyCoder, pre-trained (train = one byte per get_frequency() call)"})
+    # adversarial: always code the symbol whose interval contains the midpoint, so that E3 shifts pile up into
+    # pending runs far beyond 32 bits (src/codec.rs:75-83); then end with ordinary symbols.  Byte-aligned symbol
+    # widths only (the input is built symbol by symbol).
+    for (s, f, c), nstr in [((8, 14, 16), 12), ((8, 14, 16), 40), ((8, 22, 24), 25), ((8, 30, 32), 30), ((8, 10, 12), 60),
+                            ((8, 30, 34), 20), ((4, 10, 16), 40), ((16, 18, 20), 8)]:
+        syms, longest = straddle_symbols(s, f, c, nstr)
+        tail = [3, 1, 4, 1, 5, 9, 2, 6]
+        allsyms = syms + [t % (1 << s) for t in tail]
+        bits = "".join(format(x, "0%db" % s) for x in allsyms)
+        assert len(bits) % 8 == 0
+        data = bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8))
+        assert longest > 32, (s, f, c, longest)
+        vecs.append({"name": "straddle%d-pending%d" % (nstr, longest), "params": [s, f, c], "input": data.hex(),
+                     "compressed": PyCoder(s, f, c).encode(data).hex(),
+                     "source": "PyCoder, midpoint-straddling input (longest pending run %d)" % longest})
     with open(os.path.join(HERE, "kat_vectors.json"), "w") as fh:
         json.dump(vecs, fh, indent=0)
     print("kat_vectors.json:", len(vecs), "vectors")
+
+
+def straddle_symbols(s, f, c, n):
+    """n symbols, each chosen so that its interval contains the midpoint of the code range: the interval keeps
+    straddling one half and every renormalisation is an E3 shift.  Returns (symbols, longest pending run)."""
+    coder = PyCoder(s, f, c)
+    low, high, pending, longest = 0, coder.max, 0, 0
+    out = []
+    for _ in range(n):
+        count = coder.total
+        rng = high - low + 1
+        # the symbol with low' <= half - 1 and high' >= half, if there is one
+        pick = None
+        cum = 0
+        for sym in range(coder.eof):          # data symbols only
+            lo_, hi_ = cum, cum + coder.freq[sym]
+            cum = hi_
+            l2 = low + rng * lo_ // count
+            h2 = low + rng * hi_ // count - 1
+            if l2 < coder.half <= h2:
+                pick = sym
+                break
+        if pick is None:
+            pick = 0
+        cl, ch = coder._lookup_then_update(pick)
+        high = low + rng * ch // count - 1
+        low = low + rng * cl // count
+        while True:
+            if high < coder.half or low >= coder.half:
+                pending = 0
+            elif low >= coder.q and high < coder.q3:
+                pending += 1
+                longest = max(longest, pending)
+                low -= coder.q
+                high -= coder.q
+            else:
+                break
+            high = ((high << 1) + 1) & coder.max
+            low = (low << 1) & coder.max
+        out.append(pick)
+    return out, longest
 
 
 def make_bitio():

@@ -170,8 +170,9 @@ def test_truncated_streams_and_full_sinks(emu):
 
 
 def test_long_pending_runs(emu):
-    """Inputs built to sit on the interval midpoint produce E3 (pending) runs beyond 32 bits
-    (src/codec.rs:75-83); the packer's slow path must give the oracle's bytes."""
+    """Inputs alternating around the interval midpoint keep the coder in E3 shifts (src/codec.rs:75-83; pending
+    runs of ~10 bits here).  Runs far beyond 32 bits -- the packers' slow paths -- come from the adversarial
+    `straddle*` golden vectors (tests/golden/make_golden.py), checked in test_kernels_equal_the_golden_vectors."""
     rng = np.random.default_rng(5)
     blocks = []
     for f, c in ((14, 16), (22, 24), (30, 32)):
