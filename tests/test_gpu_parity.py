@@ -430,3 +430,40 @@ def test_multi_device_context_shards_by_block_ranges():
             b = data[int(off[i]):int(off[i + 1])]
             want = o.compress_trained(b, train, o.TREE, params)[1] if trained else o.compress(b, o.TREE, params)[1]
             assert comp[int(coff[i]):int(coff[i + 1])].tobytes() == want, (params, i)
+
+
+def test_million_symbol_block_crosses_the_quotient_bound(ctx):
+    """A 1.15 MB block with a late freeze: the total frequency passes 2^20, where the 64-bit-product decoders
+    stop trusting the float estimate of value = X / range (lane: product-domain descent; warp: exact 64-bit
+    division).  Also a slot one byte too small: OUT_CAPACITY with the prefix in place."""
+    rng = np.random.default_rng(41)
+    big = np.concatenate([rng.integers(0, 256, 400000, dtype=np.uint8),
+                          rng.choice(np.frombuffer(b"acgt", dtype=np.uint8), 400000),
+                          np.minimum(rng.geometric(0.3, 350000) - 1, 255).astype(np.uint8)]).tobytes()
+    blocks = [big, b"short block"]
+    for params in ((8, 22, 24), (8, 30, 32)):
+        out, out_off, expect = check_encode(ctx, blocks, rb.AdaptiveTreeModel, o.TREE, params)
+        check_decode(ctx, out, out_off, blocks, rb.AdaptiveTreeModel, params)
+        model = rb.AdaptiveTreeModel(rb.Parameters(*params))
+        raw_off = np.array([0, len(big) - 1, len(big) - 1 + len(blocks[1])], dtype=np.uint64)
+        raw, raw_lens, consumed, status = ctx.decode_batch(out, out_off, raw_off, model, check=False)
+        assert [int(x) for x in status] == [rb.OUT_CAPACITY, 0]
+        assert int(raw_lens[0]) == len(big) - 1 and raw[: len(big) - 1].tobytes() == big[:-1]
+        assert raw[len(big) - 1: len(big) - 1 + len(blocks[1])].tobytes() == blocks[1]
+
+
+def test_generic_threads_reuse_their_columns():
+    """16-bit symbols: a Fenwick column is 256 KiB, so 2 GB of columns hold 8,192 threads; 9,000 blocks make
+    some threads code two blocks in turn and reset their column in between."""
+    params = (16, 18, 20)
+    n, L = 9000, 48
+    raw = rb.generate_blocks_host(3, n, L, SEED)
+    off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+    model = rb.AdaptiveTreeModel(rb.Parameters(*params))
+    with rb.Context() as c:
+        out, out_off, status = c.encode_batch(raw, off, model)
+        assert (status == 0).all()
+        for i in (0, 1, 8191, 8192, 8500, 8999):
+            assert out[int(out_off[i]):int(out_off[i + 1])].tobytes() == o.compress(raw[i * L:(i + 1) * L], o.TREE, params)[1], i
+        back, lens, cons, status = c.decode_batch(out, out_off, off, model)
+        assert (status == 0).all() and (lens == L).all() and (back[: n * L] == raw).all()
