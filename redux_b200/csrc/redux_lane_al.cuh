@@ -19,7 +19,7 @@
 //   * FULL tables (whenever the entry type can hold them): nodes store the reference's actual tree
 //     values (adaptive_tree.rs:43-45 initialises tree[i] = lowbit(i)) instead of increments, so neither
 //     the query nor the decoder's descent adds the implicit lowbit terms back.
-// Bit-exactness against the oracle is checked on the CPU by tests/test_host_emu.py (these kernels
+// Bit-exactness against the oracle is checked on the CPU by the emulation tests under tests/ (these kernels
 // compiled with g++ through a shim) and on the device by tests/test_gpu_parity.py.
 #pragma once
 #include "redux_common.cuh"

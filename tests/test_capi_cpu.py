@@ -190,9 +190,16 @@ def test_no_gpu_means_cuda_error_not_fallback():
 
 
 def test_product_package_does_not_touch_oracle():
-    """Only tests/, smoke() and bench.py's CPU legs may use oracle/."""
+    """Only tests/, smoke() and bench.py's CPU legs may use oracle/; the CPU emulation of the kernels
+    (tests/host_emu, RDX_HOST_EMU) is test infrastructure too and never part of the shipped library."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "redux_b200")):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "redux_oracle" not in text and "oracle_lib" not in text, os.path.join(dirpath, f)
+                assert "host_emu" not in text and "cuda_shim" not in text, os.path.join(dirpath, f)
+    # the shared library itself exports no emulation entry point
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "redux_b200", "libredux_b200.so")],
+                          capture_output=True, text=True).stdout
+    assert "emu_" not in syms and "oracle_" not in syms
