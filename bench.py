@@ -67,6 +67,27 @@ def ncu_capture(workload, kernel):
     return None, None
 
 
+def issue_roofline(ncu, ncu_src, n_blocks, block_len, kernel_s):
+    """The roofline that actually binds this path (north_star): warp-instruction issue.  achieved = warp
+    instructions per symbol step (committed ncu capture of this workload) x symbol steps per launch / the
+    kernel's live duration; peak = the issue rate measured on the box by scripts/issue_peak.cu."""
+    if not ncu:
+        return None
+    steps = n_blocks / 32.0 * (block_len + 1)
+    achieved = ncu["warp_inst_per_symbol_step"] * steps / kernel_s
+    out = {"bound": "per-SM warp-instruction issue (4/clk/SM), the binding resource of this path",
+           "achieved_warp_inst_per_s": round(achieved, -8), "issue_active_pct_of_peak": ncu["issue_active_pct"],
+           "warp_inst_per_symbol_step": ncu["warp_inst_per_symbol_step"], "source": ncu_src}
+    try:
+        pk = json.load(open(os.path.join(ROOT, "profiles", "r01_issue_peak.json")))
+        peak = pk["issue_measured_warp_inst_per_s"]["alu_only"]
+        out.update({"peak_warp_inst_per_s": peak, "frac": round(achieved / peak, 4),
+                    "peak_source": "measured: profiles/r01_issue_peak.json (scripts/issue_peak.cu)"})
+    except Exception:
+        pass
+    return out
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -341,10 +362,7 @@ def run_ours(a):
                 "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": ncu["traffic"] if ncu else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_ms": {k: (round(v * 1e3, 3) if v else None) for k, v in kdur.items()},
-                "issue": ({"bound": "per-SM warp-instruction issue (4/clk/SM), the binding resource of this path",
-                           "issue_active_pct_of_peak": ncu["issue_active_pct"],
-                           "warp_inst_per_symbol_step": ncu["warp_inst_per_symbol_step"],
-                           "source": ncu_src} if ncu else None),
+                "issue": issue_roofline(ncu, ncu_src, n, L, kdur[dom]),
                 "note": "HBM is not the binding resource: a stream is a serial dependency chain, so the kernels "
                         "are bound by instruction issue / latency; frac is reported against HBM as the contract asks"}
 
