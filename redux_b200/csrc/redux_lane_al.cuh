@@ -179,11 +179,13 @@ struct LaneTable2 : LaneTable<TW> {
     __device__ __forceinline__ void query_frozen(uint32_t s, uint32_t cum256, uint32_t &cl, uint32_t &ch) const {
         uint32_t lo, hi;
         if (sizeof(TW) == 2) {
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(t);
-            const uint32_t w0 = w[(s >> 1) << 5], w1 = w[(((s + 1) >> 1) & 127u) << 5];
-            const bool odd = s & 1u;
-            lo = odd ? (w0 >> 16) : (w0 & 0xFFFFu);
-            hi = odd ? (w1 & 0xFFFFu) : (w0 >> 16);
+            // C[s] sits at byte (s >> 1) * 128 + (s & 1) * 2 of the lane's column; C[s+1] two bytes further for an
+            // even s, in the next word row (126 bytes further) for an odd one.  For s = 255 that is the padded row
+            // after the table: loaded, never used.
+            const uint32_t odd = s & 1u;
+            const uint8_t *pb = reinterpret_cast<const uint8_t *>(t) + (((s << 6) & 0x3F80u) | (odd << 1));
+            lo = *reinterpret_cast<const uint16_t *>(pb);
+            hi = *reinterpret_cast<const uint16_t *>(pb + (odd ? 126 : 2));
         } else {
             lo = t[s << 5];
             hi = t[((s + 1) & 255u) << 5];
