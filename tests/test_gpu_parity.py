@@ -467,3 +467,25 @@ def test_generic_threads_reuse_their_columns():
             assert out[int(out_off[i]):int(out_off[i + 1])].tobytes() == o.compress(raw[i * L:(i + 1) * L], o.TREE, params)[1], i
         back, lens, cons, status = c.decode_batch(out, out_off, off, model)
         assert (status == 0).all() and (lens == L).all() and (back[: n * L] == raw).all()
+
+
+def test_pretrained_model_with_totals_beyond_u16(ctx):
+    """A model trained on 70,000 symbols (total 70,257 > 65,535): the tuned lane kernels start from u32 table
+    entries; with freq_bits = 16 the same training freezes the model before the first coded symbol."""
+    rng = np.random.default_rng(99)
+    train = [int(x) for x in rng.integers(60, 70, 70000)]
+    blocks = [bytes(rng.integers(55, 75, n, dtype=np.uint8)) for n in (0, 1, 1000, 20000)] + [bytes([255] * 300)]
+    for params in ((8, 30, 32), (8, 22, 24), (8, 16, 18)):
+        model = rb.AdaptiveTreeModel(rb.Parameters(*params)).train(train)
+        assert model.total_frequency() == min(257 + len(train), (1 << params[1]) - 1)
+        data, off = concat(blocks)
+        out, out_off, status = ctx.encode_batch(data, off, model)
+        assert (status == 0).all()
+        raw_off = np.zeros(len(blocks) + 1, dtype=np.uint64)
+        np.cumsum(np.array([len(b) for b in blocks], dtype=np.uint64), out=raw_off[1:])
+        raw, raw_lens, consumed, status = ctx.decode_batch(out, out_off, raw_off, model)
+        assert (status == 0).all()
+        for i, b in enumerate(blocks):
+            want = o.compress_trained(b, train, o.TREE, params)[1]
+            assert out[int(out_off[i]):int(out_off[i + 1])].tobytes() == want, (params, i)
+            assert raw[int(raw_off[i]):int(raw_off[i]) + len(b)].tobytes() == b and int(consumed[i]) == len(want)
