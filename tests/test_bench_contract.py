@@ -1,0 +1,49 @@
+"""bench.py's JSON line against the driver's contract, checked on the committed record of the last GPU run
+(profiles/r01_final4_bench_default.json, profiles/r01_final4_bench_reference_arm.json).  No GPU needed."""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASELINE = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+
+
+def _load(name):
+    return json.load(open(os.path.join(ROOT, "profiles", name)))
+
+
+def test_our_arm_line_has_every_contract_key():
+    d = _load("r01_final4_bench_default.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["unit"] == "MB/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["vs_baseline"] is None and BASELINE["published"] == {}          # no published number to compare with
+    assert d["data"] == "synthetic" and "workload" in d["config"] and "65536 x 65536" in d["config"]["workload"]
+    assert d["warmup"] >= 3 and d["n_gpus"] == 1 and d["gpu_launches"] > 0
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-3
+    assert r["traffic"] is None or r["traffic"] >= r["algorithmic_bytes_per_launch"] * 0.9
+    c = d["cpu_baseline"]
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in c, k
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1
+    e = d["e2e"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in e, k
+    assert e["h2d_bytes_per_step"] > d["config"]["per_gpu_raw_bytes"] and e["value"] < d["value"]
+    assert e["value"] > 50 * c["value"]                                      # the GPU path end to end vs the host cores
+    k = d["clocks"]
+    assert not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert k["sm_mhz"] and k["sm_mhz"] > 0.9 * k["sm_max_mhz"]
+
+
+def test_reference_arm_line():
+    d = _load("r01_final4_bench_reference_arm.json")
+    assert d["impl"] == "reference" and d["unit"] == "MB/s" and d["gpu_launches"] == 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    ours = _load("r01_final4_bench_default.json")
+    assert d["metric"] == ours["metric"] and d["config"]["workload"] == ours["config"]["workload"]
