@@ -276,20 +276,29 @@ struct ByteSource2 {
         z = q3;
         w >>= 8 * (pos & 3);
     }
+    __device__ __forceinline__ void rotate() {            // pos just reached a word boundary
+        if ((pos & 15) == 0) {
+            w = n0; x = n1; y = n2; z = n3;
+            fetch(ci);
+            ++ci;
+        } else {
+            w = x; x = y; y = z;
+        }
+    }
     __device__ __forceinline__ uint32_t next() {
         const uint32_t sym = w & 0xFFu;
         w >>= 8;
         ++pos;
-        if ((pos & 3) == 0) {
-            if ((pos & 15) == 0) {
-                w = n0; x = n1; y = n2; z = n3;
-                fetch(ci);
-                ++ci;
-            } else {
-                w = x; x = y; y = z;
-            }
-        }
+        if ((pos & 3) == 0) rotate();
         return sym;
+    }
+    // the next four symbols at once (byte j = symbol j); only when the position is word aligned
+    __device__ __forceinline__ bool word_aligned() const { return (pos & 3) == 0; }
+    __device__ __forceinline__ uint32_t take_word() {
+        const uint32_t v = w;
+        pos += 4;
+        rotate();
+        return v;
     }
 };
 
@@ -346,19 +355,28 @@ encode_lane_al_kernel(const LaneEncJob job)
     uint32_t L = 0, H = 0xFFFFFFFFu;                       // low = 0, high = code_max (src/codec.rs:30-31)
     uint32_t pend = 0;
 
+    // Both phases walk the input word by word once the position is word aligned: the four symbols of a
+    // word are extracted with constant byte selectors and the per-symbol position bookkeeping disappears.
     // adaptive phase: the model still learns, count grows by one per symbol
     const uint32_t n_adapt = len < tcap ? len : tcap;
     uint32_t t = 0;
     M gn = C::ldm(magic);                                  // reciprocal of position t, loaded one ahead
-    for (; t < n_adapt; ++t) {
+    auto adapt_step = [&](uint32_t sym) {
         const M g = gn;
         gn = C::ldm(magic + t + 1);
-        const uint32_t sym = src.next();
         uint32_t cl, ch;
         // cum(256) = total - freq(EOF); increments-only tables (fresh models only) keep the 256 implicit
         tab.template query<true>(sym, count0 + t - eof_freq - (FULL ? 0u : 256u), cl, ch);
         encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, count0 + t, g, sh, one);
+        ++t;
+    };
+    while (t < n_adapt && !src.word_aligned()) adapt_step(src.next());
+    while (t + 4 <= n_adapt) {
+        const uint32_t wv = src.take_word();
+        adapt_step(__byte_perm(wv, 0, 0x4440)); adapt_step(__byte_perm(wv, 0, 0x4441));
+        adapt_step(__byte_perm(wv, 0, 0x4442)); adapt_step(__byte_perm(wv, 0, 0x4443));
     }
+    while (t < n_adapt) adapt_step(src.next());
     // frozen phase (adaptive_tree.rs:84): total == FMAX, table and reciprocal are constant
     const M gf = gn;                                       // = magic[n_adapt]
     const uint32_t countf = count0 + n_adapt;
@@ -369,13 +387,21 @@ encode_lane_al_kernel(const LaneEncJob job)
         // symbol t, so the shared-memory latency overlaps the range update
         uint32_t cl, ch;
         tab.query_frozen(src.next(), cum256f, cl, ch);
-        for (; t + 1 < len; ++t) {
+        ++t;                                               // t = symbols looked up so far
+        auto frozen_step = [&](uint32_t sym) {             // codes the symbol looked up before, looks `sym` up
             const uint32_t cl_cur = cl, ch_cur = ch;
-            tab.query_frozen(src.next(), cum256f, cl, ch);
+            tab.query_frozen(sym, cum256f, cl, ch);
             encode_step_al<CLS, C32>(L, H, pend, sink, cl_cur, ch_cur, countf, gf, sh, one);
+            ++t;
+        };
+        while (t < len && !src.word_aligned()) frozen_step(src.next());
+        while (t + 4 <= len) {
+            const uint32_t wv = src.take_word();
+            frozen_step(__byte_perm(wv, 0, 0x4440)); frozen_step(__byte_perm(wv, 0, 0x4441));
+            frozen_step(__byte_perm(wv, 0, 0x4442)); frozen_step(__byte_perm(wv, 0, 0x4443));
         }
+        while (t < len) frozen_step(src.next());
         encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, countf, gf, sh, one);
-        ++t;
     }
     // EOF symbol: [cum(256), total), then the tail of src/codec.rs:91-99: the remaining `extra` MSBs of
     // low, the first of them carrying the pending run, then flush
