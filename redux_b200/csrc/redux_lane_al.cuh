@@ -463,19 +463,13 @@ struct LaneDecoderAl {
     uint32_t count0, eof_freq;   // start total / frequency of EOF (257 / 1 for a fresh model)
     int32_t st;          // 0 running, -1 EOF symbol decoded (success), >0 error code
 
-    // Decodes symbols while t < t_end.  ADAPT: the model still learns (count = 257 + t, one reciprocal per
-    // position); otherwise the table is frozen at `count_frozen`.  PEEK: the output slot is full -- decode
-    // one more symbol only to tell a complete stream (EOF next) from Err(Eof) and from OUT_CAPACITY.
+    // One symbol (src/codec.rs:123-161).  Returns false when the stream ends here -- EOF symbol decoded
+    // (st = -1), bits ran out (st = 1) or, when PEEK, a data symbol with nowhere to go (st = 6) -- and true
+    // with the symbol in `sym_out` and every state register advanced otherwise.
     template <bool ADAPT, bool PEEK>
-    __device__ __forceinline__ void run(uint32_t t_end, const M *magic, uint32_t count_frozen, const M &g_frozen) {
-        M gn = ADAPT ? C::ldm(magic + t) : g_frozen;          // reciprocal of position t, loaded one ahead
-        // frozen table: the three nodes of the first descent round (128, 64, 192) never change -- keep them
-        // in registers and take one shared-memory round trip off every symbol's chain
-        uint32_t top_a = 0, top_b = 0, top_c = 0;
-        if (!ADAPT && CLS == kNarrow) {
-            top_a = tab.t[128 << 5]; top_b = tab.t[64 << 5]; top_c = tab.t[192 << 5];
-        }
-        while (t < t_end) {
+    __device__ __forceinline__ bool step(uint32_t &sym_out, M &gn, const M *magic, uint32_t count_frozen,
+                                         uint32_t top_a, uint32_t top_b, uint32_t top_c) {
+        {
             const uint32_t count = ADAPT ? count0 + t : count_frozen;
             const M g = gn;
             if (ADAPT && !PEEK) gn = C::ldm(magic + t + 1);
@@ -555,7 +549,7 @@ struct LaneDecoderAl {
             }
             if (is_eof) {                                         // src/codec.rs:136-138: no renorm, no reads
                 st = -1;
-                return;
+                return false;
             }
             const uint32_t sym = I >> 5;
             // src/codec.rs:133-134
@@ -566,8 +560,8 @@ struct LaneDecoderAl {
             const uint32_t n1 = common_prefix<C32>(~(l2 ^ nh2));
             const uint32_t k = clz_nz(~shl_c((l2 & nh2) << 1, n1));
             const uint32_t n = n1 + k;
-            if (n > left) { st = 1; left = 0; return; }           // Err(Eof) inside get_bit (:49-52)
-            if (PEEK) { st = 6; return; }                         // a data symbol with nowhere to go
+            if (n > left) { st = 1; left = 0; return false; }     // Err(Eof) inside get_bit (:49-52)
+            if (PEEK) { st = 6; return false; }                   // a data symbol with nowhere to go
             left -= n;
             // E1/E2: shift the window, pulling the next stream bits in; E3: keep the MSB, drop k bits below it
             const uint32_t win = bw.win();
@@ -577,8 +571,49 @@ struct LaneDecoderAl {
             bw.advance(n);
             L = shl_c(l2, n) & 0x7FFFFFFFu;
             H = ~shl_c(nh2, n) | 0x80000000u;
-            out.put(sym);
+            sym_out = sym;
             ++t;
+            return true;
+        }
+    }
+
+    // Decodes symbols while t < t_end.  ADAPT: the model still learns (count = count0 + t, one reciprocal per
+    // position); otherwise the table is frozen at `count_frozen`.  PEEK: the output slot is full -- decode
+    // one more symbol only to tell a complete stream (EOF next) from Err(Eof) and from OUT_CAPACITY.
+    // Once the output position is word aligned the loop runs four symbols per round: their bytes go to
+    // constant positions of one store and the per-symbol sink and loop bookkeeping disappears.
+    template <bool ADAPT, bool PEEK>
+    __device__ __forceinline__ void run(uint32_t t_end, const M *magic, uint32_t count_frozen, const M &g_frozen) {
+        M gn = ADAPT ? C::ldm(magic + t) : g_frozen;          // reciprocal of position t, loaded one ahead
+        // frozen table: the three nodes of the first descent round (128, 64, 192) never change -- keep them
+        // in registers and take one shared-memory round trip off every symbol's chain
+        uint32_t top_a = 0, top_b = 0, top_c = 0;
+        if (!ADAPT && CLS == kNarrow) {
+            top_a = tab.t[128 << 5]; top_b = tab.t[64 << 5]; top_c = tab.t[192 << 5];
+        }
+        uint32_t sym = 0;
+        if (PEEK) {
+            if (t < t_end) (void)step<ADAPT, true>(sym, gn, magic, count_frozen, top_a, top_b, top_c);
+            return;
+        }
+        while (t < t_end && !out.word_aligned()) {
+            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) return;
+            out.put(sym);
+        }
+        while (t + 4 <= t_end) {
+            uint32_t wv;
+            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) return;
+            wv = sym;
+            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) { out.partial(wv, 1); return; }
+            wv |= sym << 8;
+            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) { out.partial(wv, 2); return; }
+            wv |= sym << 16;
+            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) { out.partial(wv, 3); return; }
+            out.put_word(wv | (sym << 24));
+        }
+        while (t < t_end) {
+            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) return;
+            out.put(sym);
         }
     }
 };

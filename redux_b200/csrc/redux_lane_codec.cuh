@@ -458,6 +458,11 @@ struct ByteSink {
     __device__ __forceinline__ void finish() const {
         if (sh) store_bytes(pw > dst ? pw : dst, pw + (sh >> 3));
     }
+    // word-at-a-time interface (tuned decoder): valid once the position is word aligned, which also means the
+    // slot's unaligned head is behind us
+    __device__ __forceinline__ bool word_aligned() const { return sh == 0; }
+    __device__ __forceinline__ void put_word(uint32_t wv) { *reinterpret_cast<uint32_t *>(pw) = wv; pw += 4; }
+    __device__ __forceinline__ void partial(uint32_t wv, uint32_t nbytes) { wacc = wv; sh = 8 * nbytes; }   // finish() stores them
 };
 
 // ------------------------------------------------------------------ decoder
