@@ -1,5 +1,5 @@
 """bench.py's JSON line against the driver's contract, checked on the committed record of the last GPU run
-(profiles/r01_final4_bench_default.json, profiles/r01_final4_bench_reference_arm.json).  No GPU needed."""
+(profiles/r01_final5_bench_default.json, profiles/r01_final5_bench_reference_arm.json).  No GPU needed."""
 import json
 import os
 
@@ -12,7 +12,7 @@ def _load(name):
 
 
 def test_our_arm_line_has_every_contract_key():
-    d = _load("r01_final4_bench_default.json")
+    d = _load("r01_final5_bench_default.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
@@ -40,10 +40,10 @@ def test_our_arm_line_has_every_contract_key():
 
 
 def test_reference_arm_line():
-    d = _load("r01_final4_bench_reference_arm.json")
+    d = _load("r01_final5_bench_reference_arm.json")
     assert d["impl"] == "reference" and d["unit"] == "MB/s" and d["gpu_launches"] == 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
-    ours = _load("r01_final4_bench_default.json")
+    ours = _load("r01_final5_bench_default.json")
     assert d["metric"] == ours["metric"] and d["config"]["workload"] == ours["config"]["workload"]
