@@ -193,6 +193,9 @@ uint64_t redux_debug_magic_divide(uint64_t n, uint64_t magic, uint32_t shift, in
 void redux_debug_renorm(uint64_t low, uint64_t high, uint32_t code_bits,
                         uint32_t *n1, uint32_t *k, uint64_t *new_low, uint64_t *new_high);
 
+/* Resident CTAs per SM of the tuned encoder / decoder with 16-bit tables (must be 2; needs a device). */
+int redux_debug_lane_occupancy(int *enc_ctas_per_sm, int *dec_ctas_per_sm);
+
 /* The host front end's partition rule: device g of n_devices codes blocks [first, first+count). */
 void redux_debug_shard(uint64_t n_blocks, uint32_t n_devices, uint32_t g, uint64_t *first, uint64_t *count);
 

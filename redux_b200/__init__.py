@@ -135,6 +135,7 @@ def lib():
     L.redux_debug_renorm.restype = None
     L.redux_debug_shard.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
     L.redux_debug_shard.restype = None
+    L.redux_debug_lane_occupancy.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L
 

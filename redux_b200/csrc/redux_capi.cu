@@ -142,11 +142,14 @@ cudaError_t configure_kernels()
     RDX_CFG((decode_lane_kernel<uint16_t, kHuge>), s16)   RDX_CFG((decode_lane_kernel<uint32_t, kHuge>), s32)
     // tuned kernels (redux_lane_al.cuh): <entry type, class, full tree values, code_bits == 32>.
     // NARROW (c + f <= 30) implies at most 16,126 updates: always u16 entries with full values.
-    RDX_CFG((encode_lane_al_kernel<uint16_t, kNarrow, true, false>), s16) RDX_CFG((decode_lane_al_kernel<uint16_t, kNarrow, true, false>), s16)
+    // The narrow decoder comes twice: code_bits <= 16 runs the STAGED window refill (redux_lane_al.cuh, BitWindow).
+    RDX_CFG((encode_lane_al_kernel<uint16_t, kNarrow, true, false>), s16)
+    RDX_CFG((decode_lane_al_kernel<uint16_t, kNarrow, true, false, true>), s16)
+    RDX_CFG((decode_lane_al_kernel<uint16_t, kNarrow, true, false, false>), s16)
 #define RDX_CFG_WIDE(C32) \
-    RDX_CFG((encode_lane_al_kernel<uint16_t, kWide, true, C32>), s16)  RDX_CFG((decode_lane_al_kernel<uint16_t, kWide, true, C32>), s16) \
-    RDX_CFG((encode_lane_al_kernel<uint16_t, kWide, false, C32>), s16) RDX_CFG((decode_lane_al_kernel<uint16_t, kWide, false, C32>), s16) \
-    RDX_CFG((encode_lane_al_kernel<uint32_t, kWide, true, C32>), s32)  RDX_CFG((decode_lane_al_kernel<uint32_t, kWide, true, C32>), s32)
+    RDX_CFG((encode_lane_al_kernel<uint16_t, kWide, true, C32>), s16)  RDX_CFG((decode_lane_al_kernel<uint16_t, kWide, true, C32, false>), s16) \
+    RDX_CFG((encode_lane_al_kernel<uint16_t, kWide, false, C32>), s16) RDX_CFG((decode_lane_al_kernel<uint16_t, kWide, false, C32, false>), s16) \
+    RDX_CFG((encode_lane_al_kernel<uint32_t, kWide, true, C32>), s32)  RDX_CFG((decode_lane_al_kernel<uint32_t, kWide, true, C32, false>), s32)
     RDX_CFG_WIDE(false) RDX_CFG_WIDE(true)
 #undef RDX_CFG_WIDE
 #undef RDX_CFG
@@ -157,6 +160,7 @@ cudaError_t configure_kernels()
 struct Plan {
     int cls; uint32_t f, c, tcap; bool wide_table; uint32_t magic_len; uint64_t slot_stride;
     bool aligned = false, full_table = false;   // see LanePlan
+    uint64_t gf_m = 0; uint32_t gf_sh = 0;      // see LanePlan
     // generic path (redux_generic_codec.cuh): symbol_bits != 8 or a pre-trained model
     bool generic = false; uint32_t s = 8, gen_threads = 0, gen_total = 0;
     // byte symbols, code_bits <= 32, model trained before the call: the tuned lane kernels start from its tree
@@ -232,6 +236,7 @@ int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, P
     pl->f = lp.f; pl->c = lp.c; pl->cls = lp.cls; pl->tcap = lp.tcap; pl->wide_table = lp.wide_table;
     pl->magic_len = lp.magic_len; pl->slot_stride = lp.slot_stride;
     pl->aligned = lp.aligned; pl->full_table = lp.full_table;
+    pl->gf_m = lp.gf_m; pl->gf_sh = lp.gf_sh;
     return REDUX_OK;
 }
 
@@ -243,7 +248,9 @@ int get_magic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const Plan &p
     for (auto &m : d->magics)
         if (m.cls == pl.cls && m.nbits == nbits && m.len >= pl.magic_len) { *out = m.ptr; return REDUX_OK; }
     const size_t esz = pl.cls == kNarrow ? sizeof(Magic32) : sizeof(Magic64);
-    const uint32_t len = std::max<uint32_t>(pl.magic_len, 1024);
+    // + 64: split_coder_kernel prefetches whole rounds of 32 positions and may index up to 63 entries past the
+    // last position it uses (values never consumed, but the reads must stay inside the allocation)
+    const uint32_t len = std::max<uint32_t>(pl.magic_len, 1024) + 64;
     void *ptr = nullptr;
     CU_TRY(ctx, cudaMalloc(&ptr, esz * len));
     const uint32_t threads = 256, grid = (len + threads - 1) / threads;
@@ -331,9 +338,9 @@ void launch_encode_wide(const Plan &pl, const LaneEncJob &job, uint32_t grid, si
 template <bool C32>
 void launch_decode_wide(const Plan &pl, const LaneDecJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {
-    if (pl.wide_table)       decode_lane_al_kernel<uint32_t, kWide, true, C32><<<grid, kLaneThreads, smem, s>>>(job);
-    else if (pl.full_table)  decode_lane_al_kernel<uint16_t, kWide, true, C32><<<grid, kLaneThreads, smem, s>>>(job);
-    else                     decode_lane_al_kernel<uint16_t, kWide, false, C32><<<grid, kLaneThreads, smem, s>>>(job);
+    if (pl.wide_table)       decode_lane_al_kernel<uint32_t, kWide, true, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (pl.full_table)  decode_lane_al_kernel<uint16_t, kWide, true, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
+    else                     decode_lane_al_kernel<uint16_t, kWide, false, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
 }
 void launch_encode_al(const Plan &pl, const LaneEncJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {
@@ -343,7 +350,10 @@ void launch_encode_al(const Plan &pl, const LaneEncJob &job, uint32_t grid, size
 }
 void launch_decode_al(const Plan &pl, const LaneDecJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {
-    if (pl.cls == kNarrow) decode_lane_al_kernel<uint16_t, kNarrow, true, false><<<grid, kLaneThreads, smem, s>>>(job);
+    if (pl.cls == kNarrow) {
+        if (pl.c <= 16) decode_lane_al_kernel<uint16_t, kNarrow, true, false, true><<<grid, kLaneThreads, smem, s>>>(job);
+        else            decode_lane_al_kernel<uint16_t, kNarrow, true, false, false><<<grid, kLaneThreads, smem, s>>>(job);
+    }
     else if (pl.c == 32)   launch_decode_wide<true>(pl, job, grid, smem, s);
     else                   launch_decode_wide<false>(pl, job, grid, smem, s);
 }
@@ -496,6 +506,24 @@ extern "C" void redux_debug_shard(uint64_t n_blocks, uint32_t n_devices, uint32_
     *first = a; *count = b - a;
 }
 
+// Resident CTAs per SM of the headline kernels (u16 tables).  The shared-memory budget is exact to the byte
+// (redux_lane_codec.cuh, kTabPadBytes): anything but 2 means a change pushed a kernel over it and halved the
+// number of resident streams.  Needs a device.
+extern "C" int redux_debug_lane_occupancy(int *enc_ctas_per_sm, int *dec_ctas_per_sm)
+{
+    if (!enc_ctas_per_sm || !dec_ctas_per_sm) return REDUX_INVALID_INPUT;
+    if (configure_kernels() != cudaSuccess) { (void)cudaGetLastError(); return REDUX_CUDA_ERROR; }
+    const size_t s16 = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * 2 + kTabPadBytes;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(enc_ctas_per_sm, encode_lane_al_kernel<uint16_t, kNarrow, true, false>,
+                                                      kLaneThreads, s16) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(dec_ctas_per_sm, decode_lane_al_kernel<uint16_t, kNarrow, true, false, true>,
+                                                      kLaneThreads, s16) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return REDUX_CUDA_ERROR;
+    }
+    return REDUX_OK;
+}
+
 extern "C" void redux_generate_blocks_host(uint8_t *out, uint64_t first_block, uint64_t n_blocks,
                                            uint64_t block_len, uint64_t seed)
 {
@@ -637,6 +665,7 @@ int encode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     job.magic = lane_magic(pl, magic); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
     job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
     job.init_tree = pl.pretrained ? pl.gen_init : nullptr; job.count0 = pl.count0; job.eof_freq = pl.eof_freq;
+    job.gf_m = pl.gf_m; job.gf_sh = pl.gf_sh;
     const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
     const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2) + kTabPadBytes;
     {
@@ -687,6 +716,7 @@ int decode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
     job.status = d_status; job.magic = lane_magic(pl, magic); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
     job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
     job.init_tree = pl.pretrained ? pl.gen_init : nullptr; job.count0 = pl.count0; job.eof_freq = pl.eof_freq;
+    job.gf_m = pl.gf_m; job.gf_sh = pl.gf_sh;
     const uint32_t grid = (uint32_t)((n_blocks + kLaneThreads - 1) / kLaneThreads);
     const size_t smem = (size_t)kLaneWarpsPerCta * kTabNodes * 32 * (pl.wide_table ? 4 : 2) + kTabPadBytes;
     {

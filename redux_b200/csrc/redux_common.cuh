@@ -160,6 +160,7 @@ struct LanePlan {
     int cls; uint32_t f, c, tcap; bool wide_table; uint32_t magic_len; uint64_t slot_stride;
     bool aligned;     // c <= 32 (32-bit coder state): the tuned kernels of redux_lane_al.cuh
     bool full_table;  // table entries can hold the reference's tree values (lowbit + increments)
+    uint64_t gf_m; uint32_t gf_sh;   // reciprocal of the frozen total FMAX (classes with a reciprocal table)
 };
 // count0 = total frequency of the start model: symbol_count for a fresh one, larger for a model the caller
 // trained before the call (then the table must hold full tree values: pretrained = true).
@@ -173,11 +174,15 @@ RDX_HD LanePlan lane_plan(uint32_t f, uint32_t c, uint64_t max_block_len, uint32
     const uint64_t updates = max_block_len < pl.tcap ? max_block_len : pl.tcap;
     // u16 entries suffice while increments (fresh) / cumulative values (trained) fit
     pl.wide_table = pretrained ? (uint64_t)count0 + updates > 65535 : updates > 65536;
-    pl.magic_len = (uint32_t)(count0 - kNsym + updates) + 2;   // counts 257 .. count0 + updates, +1 read-ahead
+    // counts 257 .. count0 + updates, + the read-ahead of the word-wise loops (up to 7 positions past the end)
+    pl.magic_len = (uint32_t)(count0 - kNsym + updates) + 8;
     const uint64_t bound = ((max_block_len + 1) * (uint64_t)c + 7) / 8;
     pl.slot_stride = ((bound + 15) & ~(uint64_t)15) + 16;
     pl.aligned = pl.cls != kHuge;
     pl.full_table = pretrained || pl.wide_table || updates + 256 <= 65535;   // cum(i) <= 256 + updates must fit u16
+    pl.gf_m = 0; pl.gf_sh = 0;
+    if (pl.cls == kNarrow)    { const Magic32 g = make_magic32((uint32_t)fmax, f + c); pl.gf_m = g.m; pl.gf_sh = g.sh; }
+    else if (pl.cls == kWide) { const Magic64 g = make_magic64(fmax, f + c); pl.gf_m = g.m; pl.gf_sh = g.sh; }
     return pl;
 }
 

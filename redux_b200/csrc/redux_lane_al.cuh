@@ -240,64 +240,95 @@ struct BitSink2 {
     }
 };
 
-// ------------------------------------------------------------------ byte source (encoder input), v2
-// 16 raw bytes per refill, prefetched one chunk ahead.  The chunk is fetched as four independent 32-bit
-// loads: with one 128-bit load the register allocator kept the consumer's word register inside the load's
-// destination quad and copied the FRESH value out right after issuing the load, i.e. every refill waited
-// a full memory latency (7 % of the encoder's stall samples in profiles/r01_final_ncu_full_summary.md era captures).
-struct ByteSource2 {
-    const uint32_t *base;   // 16-byte aligned start of the stream's first chunk
-    uint32_t ci, clast;     // next chunk to prefetch / last chunk that may be read
-    uint32_t n0, n1, n2, n3;
-    uint32_t w, x, y, z;    // current word (already shifted) and the following words of the chunk
-    uint32_t pos;           // byte position (chunk-relative phase in the low 4 bits)
+// ------------------------------------------------------------------ staging slot (global -> shared, asynchronous)
+// Every stream's next input word travels through a private 4-byte shared-memory slot filled by cp.async
+// (LDGSTS) instead of through a register filled by LDG.  Why: ptxas puts every in-loop LDG on ONE scoreboard,
+// and a scoreboard is a counter -- waiting for the oldest load waits for the youngest too.  Lanes refill at
+// different symbols, so in round 1 some lane's one-step-old load was always outstanding when another lane
+// consumed its own, older word: 10-16 % of both coders' time sat on that scoreboard
+// (profiles/r01_final5_ncu_full_summary.md; the SASS with its wait masks: scripts/sass_ctl.py).  cp.async groups
+// are waited for with a DEPTH (cp.async.wait_group N leaves the N youngest groups in flight), which is
+// exactly the partial wait the register path cannot express, and the in-loop code no longer contains a
+// single LDG whose scoreboard an unrelated instruction could be made to wait on.
+struct StageSlot {
+#if defined(__CUDA_ARCH__)
+    uint32_t sa;                                            // shared-window address of this thread's slot
+    __device__ __forceinline__ void init(void *slot) { sa = (uint32_t)__cvta_generic_to_shared(slot); }
+    __device__ __forceinline__ void request(const uint32_t *g) const {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(g));
+    }
+    __device__ __forceinline__ uint32_t read() const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa));
+        return v;
+    }
+    static __device__ __forceinline__ void commit() { asm volatile("cp.async.commit_group;"); }
+    template <int KEEP> static __device__ __forceinline__ void wait() { asm volatile("cp.async.wait_group %0;" :: "n"(KEEP)); }
+#else
+    uint32_t val;                                           // host emulation: the copy completes at once
+    void init(void *) { val = 0; }
+    void request(const uint32_t *g) { val = *g; }
+    uint32_t read() const { return val; }
+    static void commit() {}
+    template <int KEEP> static void wait() {}
+#endif
+};
 
-    __device__ __forceinline__ void fetch(uint32_t c) {
-        const uint32_t *q = base + (size_t)(c < clast ? c : clast) * 4;   // past the end: re-read, never consumed
-        n0 = __ldg(q); n1 = __ldg(q + 1); n2 = __ldg(q + 2); n3 = __ldg(q + 3);
+// this thread's slot: the CTA's slots follow its kLaneWarpsPerCta tables (kTabPadBytes)
+template <typename TW>
+__device__ __forceinline__ void *lane_stage_slot(void *smem) {
+    return reinterpret_cast<uint8_t *>(smem) + (size_t)kLaneWarpsPerCta * kTabNodes * 32 * sizeof(TW) + threadIdx.x * 4;
+}
+
+// ------------------------------------------------------------------ byte source (encoder input), v3
+// Aligned 32-bit words: `cur` holds the word at the position (already shifted), the word after it is in the
+// staging slot or on its way there.  Every lane consumes exactly one word per four symbols, so the main
+// loop's refill -- wait for the slot, read it, request the next word -- comes once per word and always finds
+// a copy that was issued four symbol steps (> 1,000 cycles) earlier.
+struct ByteSource3 {
+    const uint32_t *base;   // 4-byte aligned start of the stream's first word
+    uint32_t wi, wlast;     // next word to request / last word that may be read
+    uint32_t cur;
+    uint32_t pos;           // byte position (word-relative phase in the low 2 bits)
+    StageSlot slot;
+
+    __device__ __forceinline__ void request() {
+        slot.request(base + (wi < wlast ? wi : wlast));     // past the end: re-read, never consumed
+        ++wi;
     }
-    __device__ __forceinline__ void init(const uint8_t *src, uint32_t len) {
+    __device__ __forceinline__ void init(const uint8_t *src, uint32_t len, void *slot_mem) {
         const uintptr_t a = (uintptr_t)src;
-        base = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)15);
-        pos = (uint32_t)(a & 15);
-        clast = len ? (pos + len - 1) >> 4 : 0;
-        n0 = n1 = n2 = n3 = 0;
-        uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        base = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        pos = (uint32_t)(a & 3);
+        wlast = len ? (pos + len - 1) >> 2 : 0;
+        wi = 1;
+        cur = 0;
+        slot.init(slot_mem);
         if (len) {                          // len == 0: next() is never called, nothing is loaded
-            fetch(0);
-            q0 = n0; q1 = n1; q2 = n2; q3 = n3;
-            fetch(1);
+            cur = __ldg(base) >> (8 * pos);
+            request();
+            StageSlot::commit();
         }
-        ci = 2;
-        const uint32_t ws = pos >> 2;
-        w = ws == 0 ? q0 : ws == 1 ? q1 : ws == 2 ? q2 : q3;
-        x = ws == 0 ? q1 : ws == 1 ? q2 : q3;
-        y = ws == 0 ? q2 : q3;
-        z = q3;
-        w >>= 8 * (pos & 3);
     }
-    __device__ __forceinline__ void rotate() {            // pos just reached a word boundary
-        if ((pos & 15) == 0) {
-            w = n0; x = n1; y = n2; z = n3;
-            fetch(ci);
-            ++ci;
-        } else {
-            w = x; x = y; y = z;
-        }
+    __device__ __forceinline__ void refill() {              // pos just reached a word boundary
+        StageSlot::wait<0>();
+        cur = slot.read();
+        request();
+        StageSlot::commit();
     }
     __device__ __forceinline__ uint32_t next() {
-        const uint32_t sym = w & 0xFFu;
-        w >>= 8;
+        const uint32_t sym = cur & 0xFFu;
+        cur >>= 8;
         ++pos;
-        if ((pos & 3) == 0) rotate();
+        if ((pos & 3) == 0) refill();
         return sym;
     }
     // the next four symbols at once (byte j = symbol j); only when the position is word aligned
     __device__ __forceinline__ bool word_aligned() const { return (pos & 3) == 0; }
     __device__ __forceinline__ uint32_t take_word() {
-        const uint32_t v = w;
+        const uint32_t v = cur;
         pos += 4;
-        rotate();
+        refill();
         return v;
     }
 };
@@ -348,37 +379,47 @@ encode_lane_al_kernel(const LaneEncJob job)
     const M *magic = reinterpret_cast<const M *>(job.magic);
     const uint32_t tcap = job.tcap;
 
-    ByteSource2 src;
-    src.init(job.in + off, len);
+    ByteSource3 src;
+    src.init(job.in + off, len, lane_stage_slot<TW>(smem_u4));
     BitSink2 sink;
     sink.init(job.slots + blk * job.slot_stride);
     uint32_t L = 0, H = 0xFFFFFFFFu;                       // low = 0, high = code_max (src/codec.rs:30-31)
     uint32_t pend = 0;
 
-    // Both phases walk the input word by word once the position is word aligned: the four symbols of a
-    // word are extracted with constant byte selectors and the per-symbol position bookkeeping disappears.
+    // Both phases walk the input word by word once the position is word aligned: the four symbols of a word
+    // are extracted with constant byte selectors, the per-symbol position bookkeeping disappears, and the
+    // reciprocals of the adaptive phase arrive four positions ahead of their use.
     // adaptive phase: the model still learns, count grows by one per symbol
     const uint32_t n_adapt = len < tcap ? len : tcap;
     uint32_t t = 0;
     M gn = C::ldm(magic);                                  // reciprocal of position t, loaded one ahead
-    auto adapt_step = [&](uint32_t sym) {
-        const M g = gn;
-        gn = C::ldm(magic + t + 1);
+    auto adapt_coded = [&](uint32_t sym, const M &g) {
         uint32_t cl, ch;
         // cum(256) = total - freq(EOF); increments-only tables (fresh models only) keep the 256 implicit
         tab.template query<true>(sym, count0 + t - eof_freq - (FULL ? 0u : 256u), cl, ch);
         encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, count0 + t, g, sh, one);
         ++t;
     };
+    auto adapt_step = [&](uint32_t sym) {
+        const M g = gn;
+        gn = C::ldm(magic + t + 1);
+        adapt_coded(sym, g);
+    };
     while (t < n_adapt && !src.word_aligned()) adapt_step(src.next());
-    while (t + 4 <= n_adapt) {
-        const uint32_t wv = src.take_word();
-        adapt_step(__byte_perm(wv, 0, 0x4440)); adapt_step(__byte_perm(wv, 0, 0x4441));
-        adapt_step(__byte_perm(wv, 0, 0x4442)); adapt_step(__byte_perm(wv, 0, 0x4443));
+    if (t + 4 <= n_adapt) {
+        M g0 = gn, g1 = C::ldm(magic + t + 1), g2 = C::ldm(magic + t + 2), g3 = C::ldm(magic + t + 3);
+        while (t + 4 <= n_adapt) {
+            const M m0 = C::ldm(magic + t + 4), m1 = C::ldm(magic + t + 5), m2 = C::ldm(magic + t + 6), m3 = C::ldm(magic + t + 7);
+            const uint32_t wv = src.take_word();
+            adapt_coded(__byte_perm(wv, 0, 0x4440), g0); adapt_coded(__byte_perm(wv, 0, 0x4441), g1);
+            adapt_coded(__byte_perm(wv, 0, 0x4442), g2); adapt_coded(__byte_perm(wv, 0, 0x4443), g3);
+            g0 = m0; g1 = m1; g2 = m2; g3 = m3;
+        }
+        gn = g0;
     }
     while (t < n_adapt) adapt_step(src.next());
     // frozen phase (adaptive_tree.rs:84): total == FMAX, table and reciprocal are constant
-    const M gf = gn;                                       // = magic[n_adapt]
+    const M gfz = C::mk(job.gf_m, job.gf_sh);              // reciprocal of FMAX, from the constant bank
     const uint32_t countf = count0 + n_adapt;
     const uint32_t cum256f = countf - eof_freq;
     if (t < len) {
@@ -391,7 +432,7 @@ encode_lane_al_kernel(const LaneEncJob job)
         auto frozen_step = [&](uint32_t sym) {             // codes the symbol looked up before, looks `sym` up
             const uint32_t cl_cur = cl, ch_cur = ch;
             tab.query_frozen(sym, cum256f, cl, ch);
-            encode_step_al<CLS, C32>(L, H, pend, sink, cl_cur, ch_cur, countf, gf, sh, one);
+            encode_step_al<CLS, C32>(L, H, pend, sink, cl_cur, ch_cur, countf, gfz, sh, one);
             ++t;
         };
         while (t < len && !src.word_aligned()) frozen_step(src.next());
@@ -401,8 +442,9 @@ encode_lane_al_kernel(const LaneEncJob job)
             frozen_step(__byte_perm(wv, 0, 0x4442)); frozen_step(__byte_perm(wv, 0, 0x4443));
         }
         while (t < len) frozen_step(src.next());
-        encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, countf, gf, sh, one);
+        encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, countf, gfz, sh, one);
     }
+    const M gf = n_adapt == tcap ? gfz : gn;               // reciprocal of the final total
     // EOF symbol: [cum(256), total), then the tail of src/codec.rs:91-99: the remaining `extra` MSBs of
     // low, the first of them carrying the pending run, then flush
     const uint32_t shifts = encode_step_al<CLS, C32>(L, H, pend, sink, cum256f, countf, countf, gf, sh, one);
@@ -410,12 +452,59 @@ encode_lane_al_kernel(const LaneEncJob job)
     sink.put_code(top_bits(L, extra), extra, pend, 0);
     job.sizes[blk] = sink.finish();
     job.status[blk] = 0;
+    StageSlot::wait<0>();                                  // nothing of this thread may still be in flight at exit
 }
 
 // ------------------------------------------------------------------ bit window (decoder input)
 // w0:w1 are two consecutive big-endian stream words; win() = the 32 stream bits starting at bit `pos`
-// of w0.  The word after w1 is always already in flight (`nxt`, still in memory byte order).
+// of w0.  The word after w1 is in the staging slot (StageSlot) or on its way there: a refill reads the slot
+// and requests the following word.  EVERY step closes one cp.async group, refill or not, so "my word was
+// requested at least two steps ago" translates to "all but the youngest group have landed":
+// advance<KEEP = 1> never waits for a copy younger than two symbol steps.  That holds when a lane cannot
+// refill in two consecutive steps, i.e. a step consumes at most 16 bits (code_bits <= 16); wider classes use
+// KEEP = 0 (one step of distance -- their steps are twice as long).
 struct BitWindow {
+    uint32_t w0, w1, pos;
+    const uint32_t *base;
+    uint32_t idx, last;     // next word to request / last word that may be read
+    StageSlot slot;
+
+    static __device__ __forceinline__ uint32_t swap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+    __device__ __forceinline__ uint32_t word_at(uint32_t i) const { return __ldg(base + (i < last ? i : last)); }
+    __device__ __forceinline__ void request() {
+        slot.request(base + (idx < last ? idx : last));                    // past the end: re-read, never used
+        ++idx;
+    }
+    // len >= 1.  Returns the first 32 bits of the stream and leaves the window right after them.
+    __device__ __forceinline__ uint32_t init(const uint8_t *src, uint32_t len, void *slot_mem) {
+        const uintptr_t a = (uintptr_t)src;
+        const uint32_t mis = (uint32_t)(a & 3);
+        base = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        last = ((mis + len + 3) >> 2) - 1;
+        pos = 8 * mis;
+        slot.init(slot_mem);
+        w0 = swap(word_at(0)); w1 = swap(word_at(1));
+        const uint32_t first = win();
+        w0 = w1; w1 = swap(word_at(2));
+        idx = 3;
+        request();
+        StageSlot::commit();
+        StageSlot::commit();        // an empty group: the first step may already leave one group in flight
+        return first;
+    }
+    __device__ __forceinline__ uint32_t win() const { return __funnelshift_l(w1, w0, pos); }
+    template <int KEEP>
+    __device__ __forceinline__ void advance(uint32_t n) {                   // n <= 32 (KEEP = 0) / 16 (KEEP = 1)
+        StageSlot::wait<KEEP>();
+        pos += n;
+        if (pos >= 32) { pos -= 32; w0 = w1; w1 = swap(slot.read()); request(); }
+        StageSlot::commit();
+    }
+};
+
+// Register-only variant (the word after w1 in `nxt`, loaded one refill ahead) for the warp mapping
+// (redux_warp_codec.cuh), where the window is warp-uniform: one refill cadence, nothing to decouple.
+struct BitWindowReg {
     uint32_t w0, w1, nxt, pos;
     const uint32_t *base;
     uint32_t idx, last;     // next word to prefetch / last word that may be read
@@ -426,7 +515,6 @@ struct BitWindow {
         ++idx;
         return v;
     }
-    // len >= 1.  Returns the first 32 bits of the stream and leaves the window right after them.
     __device__ __forceinline__ uint32_t init(const uint8_t *src, uint32_t len) {
         const uintptr_t a = (uintptr_t)src;
         const uint32_t mis = (uint32_t)(a & 3);
@@ -450,7 +538,8 @@ struct BitWindow {
 constexpr uint32_t kQuotientMaxCount = 1u << 20;
 
 // ------------------------------------------------------------------ decoder
-template <typename TW, int CLS, bool FULL, bool C32>
+// STG: a step never consumes more than 16 bits (code_bits <= 16), see BitWindow::advance.
+template <typename TW, int CLS, bool FULL, bool C32, bool STG>
 struct LaneDecoderAl {
     using C = Cls<CLS>;
     using P = typename C::P;
@@ -461,168 +550,218 @@ struct LaneDecoderAl {
     uint32_t L, H, V;    // left-aligned low / high (src/codec.rs:11-24) and the code-value window
     uint32_t sh, one, t, left;   // one == 1 << sh, opaque to the compiler (keeps q * one + L an IMAD)
     uint32_t count0, eof_freq;   // start total / frequency of EOF (257 / 1 for a fresh model)
+    uint32_t top_a, top_b, top_c;   // nodes 128, 64, 192 (the first descent round) live in registers
     int32_t st;          // 0 running, -1 EOF symbol decoded (success), >0 error code
 
     // One symbol (src/codec.rs:123-161).  Returns false when the stream ends here -- EOF symbol decoded
     // (st = -1), bits ran out (st = 1) or, when PEEK, a data symbol with nowhere to go (st = 6) -- and true
     // with the symbol in `sym_out` and every state register advanced otherwise.
+    // The model update (adaptive_tree.rs:83-92) needs no walk of its own: the nodes of update(s+1) are exactly
+    // the nodes at which the descent to s turned LEFT (each covers s from above; the last one is the unstored
+    // node 256), and the descent has just loaded their values -- so each left turn stores value + 1.  After a
+    // step that returns false the stream is finished, so what such a step stored no longer matters.
     template <bool ADAPT, bool PEEK>
-    __device__ __forceinline__ bool step(uint32_t &sym_out, M &gn, const M *magic, uint32_t count_frozen,
-                                         uint32_t top_a, uint32_t top_b, uint32_t top_c) {
-        {
-            const uint32_t count = ADAPT ? count0 + t : count_frozen;
-            const M g = gn;
-            if (ADAPT && !PEEK) gn = C::ldm(magic + t + 1);
-            // src/codec.rs:129-131 without the division: find i with cum(i)*range <= X < cum(i+1)*range,
-            // X = (value-low+1)*count - 1
-            const uint32_t rm1 = (H - L) >> sh;
-            const P X = C::mulr(count, (V - L) >> sh) - 1;
-            P plo = 0, phi = C::mulr(count - eof_freq, rm1);      // node 256 = cum(256) = count - freq(EOF)
-            uint32_t I = 0;                                       // i * 32
-            const bool is_eof = X >= phi;
-            if (CLS == kNarrow) {
-                // two tree levels per round (adaptive_tree.rs:119-127 unrolled by two): the candidates i+m,
-                // i+m/2 and i+m+m/2 are loaded together -- 4 dependent shared-memory round trips, not 8
+    __device__ __forceinline__ bool step(uint32_t &sym_out, const M &g, uint32_t count_frozen) {
+        constexpr bool UPD = ADAPT && !PEEK;
+        const uint32_t count = ADAPT ? count0 + t : count_frozen;
+        // src/codec.rs:129-131 without the division: find i with cum(i)*range <= X < cum(i+1)*range,
+        // X = (value-low+1)*count - 1
+        const uint32_t rm1 = (H - L) >> sh;
+        const P X = C::mulr(count, (V - L) >> sh) - 1;
+        P plo = 0, phi = C::mulr(count - eof_freq, rm1);      // node 256 = cum(256) = count - freq(EOF)
+        TW *p = tab.t;                                        // row of node i: the descent's position
+        const bool is_eof = X >= phi;
+        if (CLS == kNarrow) {
+            // two tree levels per round (adaptive_tree.rs:119-127 unrolled by two): the candidates i+m,
+            // i+m/2 and i+m+m/2 are loaded together -- 4 dependent shared-memory round trips, not 8
 #pragma unroll
-                for (int m = 128; m >= 2; m >>= 2) {
-                    const int h = m >> 1;
-                    const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;      // nodes i+1, i+3 are odd
-                    // (caching the twelve possible nodes of the second round as well was measured slower: 28.7 vs 27.4 ms)
-                    const bool cached = !ADAPT && m == 128;
-                    const uint32_t a = (FULL ? 0u : (uint32_t)m) + (cached ? top_a : tab.t[I + (uint32_t)(m << 5)]);
-                    const uint32_t b = (FULL ? 0u : (uint32_t)h) + (cached ? top_b : tab.t[(int)I + (h << 5) + oddadj]);
-                    const uint32_t cc = (FULL ? 0u : (uint32_t)h) + (cached ? top_c : tab.t[(int)I + ((m + h) << 5) + oddadj]);
-                    const P pa = C::mul_add(a, rm1, plo);
-                    const P pb = C::mul_add(b, rm1, plo);
-                    const P pc = C::mul_add(cc, rm1, pa);
-                    const bool ra = X >= pa, rb = X >= pb, rc = X >= pc;
-                    const bool r2 = ra ? rc : rb;                                   // second-level decision
-                    const P p2 = ra ? pc : pb;                                      // second-level boundary
-                    const P base = ra ? pa : plo;
-                    phi = r2 ? (ra ? phi : pa) : p2;
-                    plo = r2 ? p2 : base;
-                    I += (ra ? (uint32_t)(m << 5) : 0u) + (r2 ? (uint32_t)(h << 5) : 0u);
+            for (int m = 128; m >= 2; m >>= 2) {
+                const int h = m >> 1;
+                const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;      // nodes i+1, i+3 are odd
+                // (caching the twelve possible nodes of the second round as well was measured slower: 28.7 vs 27.4 ms)
+                const bool cached = m == 128;
+                const uint32_t ar = cached ? top_a : (uint32_t)p[m << 5];
+                const uint32_t br = cached ? top_b : (uint32_t)p[(h << 5) + oddadj];
+                const uint32_t cr = cached ? top_c : (uint32_t)p[((m + h) << 5) + oddadj];
+                const uint32_t a = (FULL ? 0u : (uint32_t)m) + ar;
+                const uint32_t b = (FULL ? 0u : (uint32_t)h) + br;
+                const uint32_t cc = (FULL ? 0u : (uint32_t)h) + cr;
+                const P pa = C::mul_add(a, rm1, plo);
+                const P pb = C::mul_add(b, rm1, plo);
+                const P pc = C::mul_add(cc, rm1, pa);
+                const bool ra = X >= pa, rb = X >= pb, rc = X >= pc;
+                const bool r2 = ra ? rc : rb;                                   // second-level decision
+                const P p2 = ra ? pc : pb;                                      // second-level boundary
+                const P base = ra ? pa : plo;
+                if (UPD) {
+                    if (cached) {
+                        top_a += ra ? 0u : 1u;
+                        top_b += (!ra && !rb) ? 1u : 0u;
+                        top_c += (ra && !rc) ? 1u : 0u;
+                    } else {
+                        if (!ra) p[m << 5] = (TW)(ar + 1u);
+                        if (ra && !rc) p[((m + h) << 5) + oddadj] = (TW)(cr + 1u);
+                        if (!ra && !rb) p[(h << 5) + oddadj] = (TW)(br + 1u);
+                    }
                 }
-            } else if (count > kQuotientMaxCount) {
-                // 64-bit products, very long streams: the plain product-domain descent
-#pragma unroll
-                for (int m = 128; m >= 2; m >>= 1) {              // even nodes i + m
-                    const uint32_t tv = (FULL ? 0u : (uint32_t)m) + tab.t[I + (uint32_t)(m << 5)];
-                    const P p = C::mul_add(tv, rm1, plo);
-                    const bool right = X >= p;
-                    if (right) { I += (uint32_t)(m << 5); plo = p; } else { phi = p; }
-                }
-                {                                                 // m = 1: odd node i + 1
-                    const uint32_t tv = (FULL ? 0u : 1u) + tab.t[(int)I + 32 + LaneTable<TW>::kOddAdj];
-                    const P p = C::mul_add(tv, rm1, plo);
-                    const bool right = X >= p;
-                    if (right) { I += 32u; plo = p; } else { phi = p; }
-                }
-            } else {
-                // 64-bit products: get the reference's value = X / range (src/codec.rs:131) FIRST -- a float
-                // estimate made exact by one remainder check -- and search in the 32-bit value domain, two
-                // tree levels per round like the narrow class.  The estimate is within one of the quotient
-                // because the quotient is < count <= 2^20: relative error 2^-24 (X) + 2^-24 (range) + 2^-22
-                // (division) keeps the absolute error below 0.4.
-                uint32_t v = (uint32_t)__fdividef(__ull2float_rn((unsigned long long)X), (float)rm1 + 1.0f);
-                const P pv = C::mulr(v, rm1);                     // v * range
-                if (pv > X) v -= 1u;                              // estimate one too high
-                else if (X - pv > (P)rm1) v += 1u;                // one too low (remainder >= range)
-                uint32_t lo = 0, hi = count - eof_freq;           // cum(i) <= v < hi tracked in the value domain
-#pragma unroll
-                for (int m = 128; m >= 2; m >>= 2) {
-                    const int h = m >> 1;
-                    const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;
-                    const uint32_t a = lo + (FULL ? 0u : (uint32_t)m) + tab.t[I + (uint32_t)(m << 5)];
-                    const uint32_t b = lo + (FULL ? 0u : (uint32_t)h) + tab.t[(int)I + (h << 5) + oddadj];
-                    const uint32_t cc = a + (FULL ? 0u : (uint32_t)h) + tab.t[(int)I + ((m + h) << 5) + oddadj];
-                    const bool ra = v >= a, rb = v >= b, rc = v >= cc;
-                    const bool r2 = ra ? rc : rb;
-                    const uint32_t p2 = ra ? cc : b;
-                    const uint32_t base = ra ? a : lo;
-                    hi = r2 ? (ra ? hi : a) : p2;
-                    lo = r2 ? p2 : base;
-                    I += (ra ? (uint32_t)(m << 5) : 0u) + (r2 ? (uint32_t)(h << 5) : 0u);
-                }
-                plo = C::mulr(lo, rm1);
-                phi = C::mulr(hi, rm1);
+                phi = r2 ? (ra ? phi : pa) : p2;
+                plo = r2 ? p2 : base;
+                p += (ra ? (m << 5) : 0) + (r2 ? (h << 5) : 0);
             }
-            if (is_eof) {                                         // src/codec.rs:136-138: no renorm, no reads
-                st = -1;
-                return false;
+        } else if (count > kQuotientMaxCount) {
+            // 64-bit products, very long streams: the plain product-domain descent
+#pragma unroll
+            for (int m = 128; m >= 2; m >>= 1) {              // even nodes i + m
+                // nodes 128, 64 and 192 are the register copies (the shared-memory ones are stale while ADAPT runs)
+                const bool low_half = p == tab.t;             // m == 64: node 64 or node 192
+                const uint32_t tr = m == 128 ? top_a : m == 64 ? (low_half ? top_b : top_c) : (uint32_t)p[m << 5];
+                const P pr = C::mul_add((FULL ? 0u : (uint32_t)m) + tr, rm1, plo);
+                const bool right = X >= pr;
+                if (UPD && !right) {
+                    if (m == 128) top_a += 1u;
+                    else if (m == 64) { if (low_half) top_b += 1u; else top_c += 1u; }
+                    else p[m << 5] = (TW)(tr + 1u);
+                }
+                if (right) { p += m << 5; plo = pr; } else { phi = pr; }
             }
-            const uint32_t sym = I >> 5;
-            // src/codec.rs:133-134
-            const uint32_t nh2 = ~((uint32_t)C::divc(phi, g, count) * one + (L - 1u));
-            const uint32_t l2 = (uint32_t)C::divc(plo, g, count) * one + L;
-            if (ADAPT && !PEEK) tab.update(sym);
-            // src/codec.rs:140-158 in closed form
-            const uint32_t n1 = common_prefix<C32>(~(l2 ^ nh2));
-            const uint32_t k = clz_nz(~shl_c((l2 & nh2) << 1, n1));
-            const uint32_t n = n1 + k;
-            if (n > left) { st = 1; left = 0; return false; }     // Err(Eof) inside get_bit (:49-52)
-            if (PEEK) { st = 6; return false; }                   // a data symbol with nowhere to go
-            left -= n;
-            // E1/E2: shift the window, pulling the next stream bits in; E3: keep the MSB, drop k bits below it
-            const uint32_t win = bw.win();
-            const uint32_t A = __funnelshift_lc(win, V, n1);
-            const uint32_t Bv = __funnelshift_lc(shl_c(win, n1), A, k);
-            V = (A & 0x80000000u) | (Bv & 0x7FFFFFFFu);
-            bw.advance(n);
-            L = shl_c(l2, n) & 0x7FFFFFFFu;
-            H = ~shl_c(nh2, n) | 0x80000000u;
-            sym_out = sym;
-            ++t;
-            return true;
+            {                                                 // m = 1: odd node i + 1
+                const uint32_t tr = p[32 + LaneTable<TW>::kOddAdj];
+                const P pr = C::mul_add((FULL ? 0u : 1u) + tr, rm1, plo);
+                const bool right = X >= pr;
+                if (UPD && !right) p[32 + LaneTable<TW>::kOddAdj] = (TW)(tr + 1u);
+                if (right) { p += 32; plo = pr; } else { phi = pr; }
+            }
+        } else {
+            // 64-bit products: get the reference's value = X / range (src/codec.rs:131) FIRST -- a float
+            // estimate made exact by one remainder check -- and search in the 32-bit value domain, two
+            // tree levels per round like the narrow class.  The estimate is within one of the quotient
+            // because the quotient is < count <= 2^20: relative error 2^-24 (X) + 2^-24 (range) + 2^-22
+            // (division) keeps the absolute error below 0.4.
+            uint32_t v = (uint32_t)__fdividef(__ull2float_rn((unsigned long long)X), (float)rm1 + 1.0f);
+            const P pv = C::mulr(v, rm1);                     // v * range
+            if (pv > X) v -= 1u;                              // estimate one too high
+            else if (X - pv > (P)rm1) v += 1u;                // one too low (remainder >= range)
+            uint32_t lo = 0, hi = count - eof_freq;           // cum(i) <= v < hi tracked in the value domain
+#pragma unroll
+            for (int m = 128; m >= 2; m >>= 2) {
+                const int h = m >> 1;
+                const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;
+                const bool cached = m == 128;
+                const uint32_t ar = cached ? top_a : (uint32_t)p[m << 5];
+                const uint32_t br = cached ? top_b : (uint32_t)p[(h << 5) + oddadj];
+                const uint32_t cr = cached ? top_c : (uint32_t)p[((m + h) << 5) + oddadj];
+                const uint32_t a = lo + (FULL ? 0u : (uint32_t)m) + ar;
+                const uint32_t b = lo + (FULL ? 0u : (uint32_t)h) + br;
+                const uint32_t cc = a + (FULL ? 0u : (uint32_t)h) + cr;
+                const bool ra = v >= a, rb = v >= b, rc = v >= cc;
+                const bool r2 = ra ? rc : rb;
+                const uint32_t p2 = ra ? cc : b;
+                const uint32_t base = ra ? a : lo;
+                if (UPD) {
+                    if (cached) {
+                        top_a += ra ? 0u : 1u;
+                        top_b += (!ra && !rb) ? 1u : 0u;
+                        top_c += (ra && !rc) ? 1u : 0u;
+                    } else {
+                        if (!ra) p[m << 5] = (TW)(ar + 1u);
+                        if (ra && !rc) p[((m + h) << 5) + oddadj] = (TW)(cr + 1u);
+                        if (!ra && !rb) p[(h << 5) + oddadj] = (TW)(br + 1u);
+                    }
+                }
+                hi = r2 ? (ra ? hi : a) : p2;
+                lo = r2 ? p2 : base;
+                p += (ra ? (m << 5) : 0) + (r2 ? (h << 5) : 0);
+            }
+            plo = C::mulr(lo, rm1);
+            phi = C::mulr(hi, rm1);
         }
+        if (is_eof) {                                         // src/codec.rs:136-138: no renorm, no reads
+            st = -1;
+            return false;
+        }
+        const uint32_t sym = (uint32_t)(p - tab.t) >> 5;
+        // src/codec.rs:133-134
+        const uint32_t nh2 = ~((uint32_t)C::divc(phi, g, count) * one + (L - 1u));
+        const uint32_t l2 = (uint32_t)C::divc(plo, g, count) * one + L;
+        // src/codec.rs:140-158 in closed form
+        const uint32_t n1 = common_prefix<C32>(~(l2 ^ nh2));
+        const uint32_t k = clz_nz(~shl_c((l2 & nh2) << 1, n1));
+        const uint32_t n = n1 + k;
+        if (n > left) { st = 1; left = 0; return false; }     // Err(Eof) inside get_bit (:49-52)
+        if (PEEK) { st = 6; return false; }                   // a data symbol with nowhere to go
+        left -= n;
+        // E1/E2: shift the window, pulling the next stream bits in; E3: keep the MSB, drop k bits below it
+        const uint32_t win = bw.win();
+        const uint32_t A = __funnelshift_lc(win, V, n1);
+        const uint32_t Bv = __funnelshift_lc(shl_c(win, n1), A, k);
+        V = (A & 0x80000000u) | (Bv & 0x7FFFFFFFu);
+        bw.template advance<STG ? 1 : 0>(n);
+        L = shl_c(l2, n) & 0x7FFFFFFFu;
+        H = ~shl_c(nh2, n) | 0x80000000u;
+        sym_out = sym;
+        ++t;
+        return true;
     }
 
     // Decodes symbols while t < t_end.  ADAPT: the model still learns (count = count0 + t, one reciprocal per
-    // position); otherwise the table is frozen at `count_frozen`.  PEEK: the output slot is full -- decode
-    // one more symbol only to tell a complete stream (EOF next) from Err(Eof) and from OUT_CAPACITY.
+    // position, loaded four positions ahead in the main loop); otherwise the table is frozen at `count_frozen`.
+    // PEEK: the output slot is full -- decode one more symbol only to tell a complete stream (EOF next) from
+    // Err(Eof) and from OUT_CAPACITY.
     // Once the output position is word aligned the loop runs four symbols per round: their bytes go to
     // constant positions of one store and the per-symbol sink and loop bookkeeping disappears.
     template <bool ADAPT, bool PEEK>
     __device__ __forceinline__ void run(uint32_t t_end, const M *magic, uint32_t count_frozen, const M &g_frozen) {
-        M gn = ADAPT ? C::ldm(magic + t) : g_frozen;          // reciprocal of position t, loaded one ahead
-        // frozen table: the three nodes of the first descent round (128, 64, 192) never change -- keep them
-        // in registers and take one shared-memory round trip off every symbol's chain
-        uint32_t top_a = 0, top_b = 0, top_c = 0;
-        if (!ADAPT && CLS == kNarrow) {
-            top_a = tab.t[128 << 5]; top_b = tab.t[64 << 5]; top_c = tab.t[192 << 5];
-        }
+        // the three nodes of the first descent round (128, 64, 192) live in registers: one shared-memory round
+        // trip off every symbol's chain; the adaptive phase counts into them and writes them back at the end
+        top_a = tab.t[128 << 5]; top_b = tab.t[64 << 5]; top_c = tab.t[192 << 5];
         uint32_t sym = 0;
         if (PEEK) {
-            if (t < t_end) (void)step<ADAPT, true>(sym, gn, magic, count_frozen, top_a, top_b, top_c);
+            if (t < t_end) (void)step<ADAPT, true>(sym, ADAPT ? C::ldm(magic + t) : g_frozen, count_frozen);
             return;
         }
+        M gn = ADAPT ? C::ldm(magic + t) : g_frozen;          // reciprocal of position t, loaded one ahead
         while (t < t_end && !out.word_aligned()) {
-            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) return;
+            const M g = gn;
+            if (ADAPT) gn = C::ldm(magic + t + 1);
+            if (!step<ADAPT, false>(sym, g, count_frozen)) return;
             out.put(sym);
         }
-        while (t + 4 <= t_end) {
-            uint32_t wv;
-            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) return;
-            wv = sym;
-            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) { out.partial(wv, 1); return; }
-            wv |= sym << 8;
-            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) { out.partial(wv, 2); return; }
-            wv |= sym << 16;
-            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) { out.partial(wv, 3); return; }
-            out.put_word(wv | (sym << 24));
+        if (t + 4 <= t_end) {
+            M g0 = gn, g1 = gn, g2 = gn, g3 = gn;
+            if (ADAPT) { g1 = C::ldm(magic + t + 1); g2 = C::ldm(magic + t + 2); g3 = C::ldm(magic + t + 3); }
+            while (t + 4 <= t_end) {
+                M m0 = g0, m1 = g1, m2 = g2, m3 = g3;
+                if (ADAPT) {
+                    m0 = C::ldm(magic + t + 4); m1 = C::ldm(magic + t + 5); m2 = C::ldm(magic + t + 6); m3 = C::ldm(magic + t + 7);
+                }
+                uint32_t wv;
+                if (!step<ADAPT, false>(sym, g0, count_frozen)) return;
+                wv = sym;
+                if (!step<ADAPT, false>(sym, g1, count_frozen)) { out.partial(wv, 1); return; }
+                wv |= sym << 8;
+                if (!step<ADAPT, false>(sym, g2, count_frozen)) { out.partial(wv, 2); return; }
+                wv |= sym << 16;
+                if (!step<ADAPT, false>(sym, g3, count_frozen)) { out.partial(wv, 3); return; }
+                out.put_word(wv | (sym << 24));
+                if (ADAPT) { g0 = m0; g1 = m1; g2 = m2; g3 = m3; }
+            }
+            gn = g0;
         }
         while (t < t_end) {
-            if (!step<ADAPT, false>(sym, gn, magic, count_frozen, top_a, top_b, top_c)) return;
+            const M g = gn;
+            if (ADAPT) gn = C::ldm(magic + t + 1);
+            if (!step<ADAPT, false>(sym, g, count_frozen)) return;
             out.put(sym);
         }
+        if (ADAPT) { tab.t[128 << 5] = (TW)top_a; tab.t[64 << 5] = (TW)top_b; tab.t[192 << 5] = (TW)top_c; }
     }
 };
 
-template <typename TW, int CLS, bool FULL, bool C32>
+template <typename TW, int CLS, bool FULL, bool C32, bool STG>
 __global__ void __launch_bounds__(kLaneThreads, 2)
 decode_lane_al_kernel(const LaneDecJob job)
 {
-    using D = LaneDecoderAl<TW, CLS, FULL, C32>;
+    using D = LaneDecoderAl<TW, CLS, FULL, C32, STG>;
     using M = typename D::M;
     extern __shared__ uint4 smem_u4[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -655,7 +794,7 @@ decode_lane_al_kernel(const LaneDecJob job)
     if (total_bits < c) {
         d.st = 1;
     } else {
-        d.V = d.bw.init(job.comp + coff, (uint32_t)clen);
+        d.V = d.bw.init(job.comp + coff, (uint32_t)clen, lane_stage_slot<TW>(smem_u4));
         d.left = total_bits - c;
     }
     const M g0 = D::C::ldm(magic);
@@ -665,7 +804,7 @@ decode_lane_al_kernel(const LaneDecJob job)
         if (d.st == 0 && d.t == cap && cap < tcap) d.template run<true, true>(d.t + 1, magic, 0, g0);
     }
     if (d.st == 0) {
-        const M gf = D::C::ldm(magic + tcap);
+        const M gf = D::C::mk(job.gf_m, job.gf_sh);           // reciprocal of FMAX, from the constant bank
         d.template run<false, false>(cap, magic, d.count0 + tcap, gf);
         if (d.st == 0) d.template run<false, true>(d.t + 1, magic, d.count0 + tcap, gf);
     }
@@ -673,6 +812,7 @@ decode_lane_al_kernel(const LaneDecJob job)
     job.raw_len[blk] = d.t;
     job.consumed[blk] = (total_bits - d.left + 7) >> 3;
     job.status[blk] = d.st < 0 ? 0 : d.st;
+    StageSlot::wait<0>();                                  // nothing of this thread may still be in flight at exit
 }
 
 }  // namespace rdx

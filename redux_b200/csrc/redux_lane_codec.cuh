@@ -33,8 +33,11 @@ namespace rdx {
 constexpr int kLaneWarpsPerCta = 7;                 // 7 warps x 16 KiB tables; 2 CTAs per SM
 constexpr int kLaneThreads = kLaneWarpsPerCta * 32;
 constexpr int kTabNodes = 256;                      // nodes 0..255 (node 0 stays 0: the "absent" node)
-constexpr int kTabPadBytes = 128;                   // one row after the last warp's table: the tuned kernels load
-                                                    // the update path's "node 256" unconditionally (never stored)
+// After the last warp's table: one 4-byte STAGING SLOT per thread (redux_lane_al.cuh, StageSlot).  The same bytes
+// serve as the padded row the tuned kernels' unconditional load of the update path's "node 256" falls into
+// (never stored).  2 x (7 x 16 KiB + 896 B + 1 KiB reserved per CTA) = 233,216 B of the SM's 233,472: two CTAs
+// per SM, and not a byte to spare for a second slot.
+constexpr int kTabPadBytes = kLaneThreads * 4;
 
 struct LaneEncJob {
     const uint8_t *in;          // raw bytes
@@ -52,6 +55,9 @@ struct LaneEncJob {
     const uint32_t *init_tree;  // tree[0..255] of the start model (adaptive_tree.rs layout), or NULL
     uint32_t count0;            // its total frequency; `magic` entry t <-> count0 + t, tcap = FMAX - count0
     uint32_t eof_freq;          // frequency of the EOF symbol: cum(256) = total - eof_freq
+    // reciprocal of the frozen total FMAX (= magic[tcap]) as launch constants: the frozen loops read it from the
+    // constant bank, so no in-loop instruction depends on a global load's scoreboard (tuned kernels only)
+    uint64_t gf_m; uint32_t gf_sh;
 };
 
 struct LaneDecJob {
@@ -69,6 +75,7 @@ struct LaneDecJob {
     uint32_t one;               // as in LaneEncJob
     const uint32_t *init_tree;  // as in LaneEncJob
     uint32_t count0, eof_freq;
+    uint64_t gf_m; uint32_t gf_sh;   // as in LaneEncJob
 };
 
 // ------------------------------------------------------------------ arithmetic class traits
@@ -81,6 +88,7 @@ template <> struct Cls<kNarrow> {
     static __device__ __forceinline__ M ldm(const M *p) {
         uint2 v = __ldg(reinterpret_cast<const uint2 *>(p)); M g; g.m = v.x; g.sh = v.y; return g;
     }
+    static __device__ __forceinline__ M mk(uint64_t m, uint32_t sh) { M g; g.m = (uint32_t)m; g.sh = sh; return g; }
 };
 template <> struct Cls<kWide> {
     using S = uint32_t; using P = uint64_t; using M = Magic64;
@@ -91,6 +99,7 @@ template <> struct Cls<kWide> {
         uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
         M g; g.m = ((uint64_t)v.y << 32) | v.x; g.sh = v.z; g.pad = 0; return g;
     }
+    static __device__ __forceinline__ M mk(uint64_t m, uint32_t sh) { M g; g.m = m; g.sh = sh; g.pad = 0; return g; }
 };
 template <> struct Cls<kHuge> {
     using S = uint64_t; using P = uint64_t; using M = Magic64;
@@ -98,6 +107,7 @@ template <> struct Cls<kHuge> {
     static __device__ __forceinline__ P mul_add(uint32_t v, S rm1, P acc) { return (uint64_t)v * (rm1 + 1u) + acc; }
     static __device__ __forceinline__ P divc(P n, const M &, uint32_t count) { return n / count; }
     static __device__ __forceinline__ M ldm(const M *) { M g; g.m = 0; g.sh = 0; g.pad = 0; return g; }
+    static __device__ __forceinline__ M mk(uint64_t, uint32_t) { M g; g.m = 0; g.sh = 0; g.pad = 0; return g; }
 };
 
 // ------------------------------------------------------------------ Fenwick increments in smem

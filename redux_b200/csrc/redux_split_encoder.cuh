@@ -283,9 +283,12 @@ split_coder_kernel(const LaneEncJob job, const SplitJob sj)
         const uint32_t t = base + lane;
         return t < len ? pairs[t] : make_uint2(0, 1);
     };
+    // count_t = 257 + min(t, T); positions past the stream's own end (the last round is fetched whole and a
+    // full round ahead) re-read the entry of the EOF step, so no index leaves the table the plan sized
+    const uint32_t tlast = len < tcap ? len : tcap;
     auto fetch_magic = [&](uint32_t base) {
         const uint32_t t = base + lane;
-        return C::ldm(magic + (t < tcap ? t : tcap));              // count_t = 257 + min(t, T)
+        return C::ldm(magic + (t < tlast ? t : tlast));
     };
     uint2 pn = fetch_pair(0);
     M gn = fetch_magic(0);

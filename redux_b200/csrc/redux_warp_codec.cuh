@@ -362,7 +362,7 @@ decode_warp_al_kernel(const LaneDecJob job)
     uint32_t cum[8];                                               // cum(lane + 32 j); a fresh model: cum(i) = i
 #pragma unroll
     for (int j = 0; j < 8; ++j) cum[j] = lane + 32u * j;
-    BitWindow bw;
+    BitWindowReg bw;
     WarpByteSink out;
     out.init(job.raw + roff);
     out.en = lane == 0;

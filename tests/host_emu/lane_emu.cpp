@@ -99,6 +99,7 @@ extern "C" int emu_encode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len
     job.magic = shift_magic(pl, magic, st0.count0); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
     job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
     job.init_tree = st0.on ? st0.tree.data() : nullptr; job.count0 = st0.count0; job.eof_freq = st0.eof_freq;
+    job.gf_m = pl.gf_m; job.gf_sh = pl.gf_sh;
 #define RUN(TW) \
     (pl.cls == kNarrow ? run_grid(encode_lane_kernel<TW, kNarrow>, job, n_blocks) : \
      pl.cls == kWide   ? run_grid(encode_lane_kernel<TW, kWide>, job, n_blocks)   : \
@@ -141,14 +142,16 @@ extern "C" int emu_decode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len
     job.status = status; job.magic = shift_magic(pl, magic, st0.count0); job.f = pl.f; job.c = pl.c; job.tcap = pl.tcap;
     job.one = pl.c <= 32 ? 1u << (32 - pl.c) : 0u;
     job.init_tree = st0.on ? st0.tree.data() : nullptr; job.count0 = st0.count0; job.eof_freq = st0.eof_freq;
+    job.gf_m = pl.gf_m; job.gf_sh = pl.gf_sh;
 #define RUN(TW) \
     (pl.cls == kNarrow ? run_grid(decode_lane_kernel<TW, kNarrow>, job, n_blocks) : \
      pl.cls == kWide   ? run_grid(decode_lane_kernel<TW, kWide>, job, n_blocks)   : \
                          run_grid(decode_lane_kernel<TW, kHuge>, job, n_blocks))
 #define RUN_AL(TW, FULL) \
-    (pl.cls == kNarrow ? run_grid(decode_lane_al_kernel<TW, kNarrow, FULL, false>, job, n_blocks) : \
-     pl.c == 32        ? run_grid(decode_lane_al_kernel<TW, kWide, FULL, true>, job, n_blocks) : \
-                         run_grid(decode_lane_al_kernel<TW, kWide, FULL, false>, job, n_blocks))
+    (pl.cls == kNarrow && pl.c <= 16 ? run_grid(decode_lane_al_kernel<TW, kNarrow, FULL, false, true>, job, n_blocks) : \
+     pl.cls == kNarrow ? run_grid(decode_lane_al_kernel<TW, kNarrow, FULL, false, false>, job, n_blocks) : \
+     pl.c == 32        ? run_grid(decode_lane_al_kernel<TW, kWide, FULL, true, false>, job, n_blocks) : \
+                         run_grid(decode_lane_al_kernel<TW, kWide, FULL, false, false>, job, n_blocks))
     if (pl.aligned && !legacy) {
         if (pl.wide_table) RUN_AL(uint32_t, true);
         else if (pl.full_table) RUN_AL(uint16_t, true);

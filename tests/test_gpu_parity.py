@@ -398,6 +398,17 @@ def test_generic_many_blocks_share_columns(ctx):
     assert (status == 0).all() and (back[: n * L] == raw).all()      # 96 bytes = 64 whole 12-bit symbols
 
 
+def test_two_ctas_per_sm_fit_the_shared_memory_budget():
+    """The tuned kernels' shared memory (7 x 16 KiB tables + one 4-byte staging slot per thread) is sized to the
+    byte for two CTAs per SM = 448 resident streams per SM, which is what puts 65,536 blocks in ONE wave on 148
+    SMs.  One CTA per SM would silently halve the throughput."""
+    import ctypes as C
+    with rb.Context([0]):
+        enc, dec = C.c_int(0), C.c_int(0)
+        assert rb.lib().redux_debug_lane_occupancy(C.byref(enc), C.byref(dec)) == rb.OK
+        assert (enc.value, dec.value) == (2, 2)
+
+
 def test_multi_device_context_shards_by_block_ranges():
     """one context over all visible GPUs, one host thread per device, contiguous block ranges,
     no collective.  The bytes, offsets and statuses must not depend on the number of devices.  Needs >= 2 GPUs
