@@ -76,6 +76,25 @@ uint64_t redux_compress_bound(uint64_t in_len, uint32_t code_bits);
  * dropped by the reference's reader, src/bitio/mod.rs:94-108 + src/codec.rs:106-110) plus EOF. */
 uint64_t redux_compress_bound_ex(uint64_t in_len, uint32_t symbol_bits, uint32_t code_bits);
 
+/* ---- process-wide set-up (optional).  The host-buffer API pipelines ~18 CUDA streams per device; CUDA maps streams
+ * onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8), and streams that share a queue serialise.
+ * redux_process_init() sets that variable to 32 unless the application already set it, and returns the value in
+ * force.  It only has an effect BEFORE the process creates its first CUDA context, it changes the environment of
+ * the whole process, and nothing in this library calls it implicitly: an application that manages the variable
+ * itself simply does not call it (the end-to-end calls then run ~20 % slower, the results are identical). */
+int redux_process_init(void);
+
+/* ---- host memory for the host-buffer API.  redux_encode_batch / redux_decode_batch copy straight from / to the
+ * caller's pointers (the reference streams through &mut io::Read / io::Write, src/lib.rs:102-109; a binding lands
+ * that in a byte buffer).  Page-locked buffers make those copies asynchronous so the chunk
+ * pipeline overlaps them with the kernels; pageable buffers work, at roughly host-memcpy speed (bench.py reports
+ * both).  redux_host_alloc returns page-locked memory usable with every device; redux_host_register page-locks
+ * an existing allocation (e.g. a long-lived Vec<u8>) in place -- pinning costs ~0.1 ms per MiB, so do it once. */
+int redux_host_alloc(size_t bytes, void **out);
+int redux_host_free(void *p);
+int redux_host_register(void *p, size_t bytes);
+int redux_host_unregister(void *p);
+
 /* ---- context: owns per-device streams and workspaces. Not thread-safe (one caller at a time).
  * devices == NULL or n_devices <= 0: use the current device only. */
 int  redux_ctx_create(const int *devices, int n_devices, redux_ctx_t **ctx);
@@ -151,9 +170,12 @@ int redux_decode_batch_ex(redux_ctx_t *ctx, int model_kind, const redux_params_t
 
 /* ---- batch, device-resident buffers (kernel-only timing; all pointers are device memory on
  * `device`, which must be one of the context's devices; work is enqueued on `stream` (a
- * cudaStream_t; NULL = the CUDA default stream) and is asynchronous).
+ * cudaStream_t; NULL = the CUDA default stream) and is asynchronous to the host).
+ * A device has ONE workspace: a call enqueued on another stream of the same device first waits (on the device,
+ * cudaStreamWaitEvent) for the previous call's kernels, so calls never overlap on one device whatever streams
+ * they use.  Growing a workspace for a larger batch synchronises the device once.
  * max_block_len: an upper bound of every block's raw length (sizes the per-block output slots).
- * Alignment contract: the kernels read d_in / d_comp with aligned 16-byte / 4-byte vector loads, so the
+ * Alignment contract: the kernels read d_in / d_comp with aligned vector loads (at most 16 bytes), so the
  * bytes from the enclosing 16-byte boundaries of the first and last byte of each stream must be readable
  * (true for any cudaMalloc / torch allocation: granularity >= 256 B); values outside a stream are ignored.
  * total_in_bytes = in_offsets[n_blocks] as known by the host. */
@@ -169,6 +191,20 @@ int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *stream, int mo
                               uint64_t max_block_len,
                               uint8_t *d_raw, const uint64_t *d_raw_offsets, uint64_t *d_raw_lens,
                               uint64_t *d_consumed, int32_t *d_status);
+/* The same with a pre-trained start model (see redux_encode_batch_ex; model_freq is a HOST pointer, copied during
+ * the call). */
+int redux_encode_batch_device_ex(redux_ctx_t *ctx, int device, void *stream, int model_kind,
+                                 const redux_params_t *params, const uint32_t *model_freq,
+                                 const uint8_t *d_in, const uint64_t *d_in_offsets, uint64_t n_blocks,
+                                 uint64_t max_block_len,
+                                 uint8_t *d_out, uint64_t out_capacity, uint64_t *d_out_offsets,
+                                 int32_t *d_status);
+int redux_decode_batch_device_ex(redux_ctx_t *ctx, int device, void *stream, int model_kind,
+                                 const redux_params_t *params, const uint32_t *model_freq,
+                                 const uint8_t *d_comp, const uint64_t *d_comp_offsets, uint64_t n_blocks,
+                                 uint64_t max_block_len,
+                                 uint8_t *d_raw, const uint64_t *d_raw_offsets, uint64_t *d_raw_lens,
+                                 uint64_t *d_consumed, int32_t *d_status);
 /* Waits for the work enqueued on `stream` of `device`. */
 int redux_ctx_synchronize(redux_ctx_t *ctx, int device, void *stream);
 

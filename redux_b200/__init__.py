@@ -19,7 +19,7 @@ import numpy as np
 __all__ = [
     "Parameters", "AdaptiveLinearModel", "AdaptiveTreeModel", "Model", "compress", "decompress",
     "Context", "ReduxError", "Eof", "InvalidInput", "IoError", "CudaError", "Unsupported", "OutCapacity",
-    "compress_bound", "build", "lib",
+    "compress_bound", "build", "lib", "process_init", "HostBuffer", "host_register", "host_unregister",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -136,6 +136,13 @@ def lib():
     L.redux_debug_shard.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]
     L.redux_debug_shard.restype = None
     L.redux_debug_lane_occupancy.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.redux_process_init.argtypes = []
+    L.redux_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.redux_host_free.argtypes = [vp]
+    L.redux_host_register.argtypes = [vp, C.c_size_t]
+    L.redux_host_unregister.argtypes = [vp]
+    L.redux_encode_batch_device_ex.argtypes = [vp, i32, vp, i32, pp, vp, vp, vp, u64, u64, vp, u64, vp, vp]
+    L.redux_decode_batch_device_ex.argtypes = [vp, i32, vp, i32, pp, vp, vp, vp, u64, u64, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -149,6 +156,43 @@ def _raise(code, ctx=None):
         if detail:
             msg = "%s (%s)" % (msg, detail)
     raise _ERRORS.get(code, ReduxError)(msg)
+
+
+def process_init():
+    """Optional, before CUDA is initialised in this process: ask for 32 hardware queues unless the application
+    set CUDA_DEVICE_MAX_CONNECTIONS itself (include/redux_b200.h).  Returns the value in force."""
+    return int(lib().redux_process_init())
+
+
+class HostBuffer:
+    """Page-locked host memory from redux_host_alloc as a numpy uint8 array (`.array`); freed by close()."""
+
+    def __init__(self, nbytes):
+        self._p = C.c_void_p()
+        _raise(lib().redux_host_alloc(nbytes, C.byref(self._p)))
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self._p.value)) if nbytes else np.zeros(0, np.uint8)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib().redux_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def host_register(array):
+    """Page-lock an existing numpy buffer in place (redux_host_register); pair with host_unregister."""
+    _raise(lib().redux_host_register(array.ctypes.data, array.nbytes))
+
+
+def host_unregister(array):
+    _raise(lib().redux_host_unregister(array.ctypes.data))
 
 
 def compress_bound(in_len, code_bits, symbol_bits=8):
@@ -409,17 +453,17 @@ class Context:
     def encode_batch_device(self, d_in, d_in_offsets, n_blocks, max_block_len, d_out, out_capacity,
                             d_out_offsets, d_status, model, device=0, stream=None):
         pc = model.params._c()
-        _raise(lib().redux_encode_batch_device(self._h, device, stream, model.kind, C.byref(pc), _ptr(d_in),
-                                               _ptr(d_in_offsets), n_blocks, max_block_len, _ptr(d_out),
-                                               out_capacity, _ptr(d_out_offsets), _ptr(d_status)), self)
+        _raise(lib().redux_encode_batch_device_ex(self._h, device, stream, model.kind, C.byref(pc), model._freq_ptr(),
+                                                  _ptr(d_in), _ptr(d_in_offsets), n_blocks, max_block_len, _ptr(d_out),
+                                                  out_capacity, _ptr(d_out_offsets), _ptr(d_status)), self)
 
     def decode_batch_device(self, d_comp, d_comp_offsets, n_blocks, max_block_len, d_raw, d_raw_offsets,
                             d_raw_lens, d_consumed, d_status, model, device=0, stream=None):
         pc = model.params._c()
-        _raise(lib().redux_decode_batch_device(self._h, device, stream, model.kind, C.byref(pc), _ptr(d_comp),
-                                               _ptr(d_comp_offsets), n_blocks, max_block_len, _ptr(d_raw),
-                                               _ptr(d_raw_offsets), _ptr(d_raw_lens), _ptr(d_consumed),
-                                               _ptr(d_status)), self)
+        _raise(lib().redux_decode_batch_device_ex(self._h, device, stream, model.kind, C.byref(pc), model._freq_ptr(),
+                                                  _ptr(d_comp), _ptr(d_comp_offsets), n_blocks, max_block_len,
+                                                  _ptr(d_raw), _ptr(d_raw_offsets), _ptr(d_raw_lens), _ptr(d_consumed),
+                                                  _ptr(d_status)), self)
 
     def generate_blocks_device(self, d_out, first_block, n_blocks, block_len, seed, device=0, stream=None):
         _raise(lib().redux_generate_blocks_device(self._h, device, stream, _ptr(d_out), first_block, n_blocks,

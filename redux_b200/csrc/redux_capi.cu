@@ -8,6 +8,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,12 +31,15 @@ using namespace rdx;
 // The pipelined host-buffer API keeps ~18 streams busy per device.  CUDA multiplexes streams onto
 // CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue serialise in
 // submission order, which measured as three chunks of sixteen stalling ~30 ms behind unrelated copies
-// (profiles/r01_e2e_pipeline.md).  The variable is read when the CUDA context is created, so the
-// library asks for 32 queues when it is loaded -- effective whenever that happens before the process
-// initialises CUDA (import order in Python, link order in C); an explicit user setting wins.
-__attribute__((constructor)) static void redux_b200_on_load()
+// (profiles/r01_e2e_pipeline.md).  The variable is read when the process creates its first CUDA context, and
+// it is process-wide, so the library does NOT touch it on its own (round 1 did, from a load-time constructor:
+// a hidden side effect on the embedding application).  redux_process_init() is the explicit, optional form.
+extern "C" int redux_process_init(void)
 {
+    const char *cur = std::getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+    if (cur) return std::atoi(cur);                       // the application's own setting wins
     setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    return 32;
 }
 
 namespace {
@@ -85,6 +90,12 @@ struct DeviceState {
     uint8_t *text_lut = nullptr;
     std::vector<MagicEntry> magics;
     bool smem_set = false;
+    // The device-resident entry points share ONE workspace per device (slots, sizes, generic-path columns ...).
+    // Calls may arrive on different streams, so each call first makes its stream wait for the previous call's
+    // last kernel (ws_busy) and records it again when it is enqueued: at most one device call in flight per
+    // device, asynchronous to the host all the same.
+    cudaEvent_t ws_busy = nullptr;
+    bool ws_recorded = false;
 };
 
 }  // namespace
@@ -427,6 +438,18 @@ struct KernelTimer {
     ~KernelTimer() { if (on) { cudaEventRecord(span.b, s); ctx->spans.push_back(span); } }
 };
 
+// One device call in flight per device (see DeviceState::ws_busy).
+cudaError_t ws_acquire(DeviceState *d, cudaStream_t s)
+{
+    return d->ws_recorded ? cudaStreamWaitEvent(s, d->ws_busy, 0) : cudaSuccess;
+}
+cudaError_t ws_release(DeviceState *d, cudaStream_t s)
+{
+    cudaError_t e = cudaEventRecord(d->ws_busy, s);
+    if (e == cudaSuccess) d->ws_recorded = true;
+    return e;
+}
+
 }  // namespace
 
 // =============================================================================== host arithmetic
@@ -538,6 +561,37 @@ extern "C" void redux_generate_blocks_host(uint8_t *out, uint64_t first_block, u
         }
 }
 
+// =================================================================================== host memory
+// The host-buffer API copies straight from / to the caller's pointers.  From pinned (page-locked) memory the
+// copies are asynchronous and the chunk pipeline overlaps them with the kernels; from pageable memory CUDA stages
+// every copy through its own bounce buffer and the calls degrade to roughly the speed of a host memcpy.
+extern "C" int redux_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return REDUX_INVALID_INPUT;
+    *out = nullptr;
+    if (bytes == 0) return REDUX_OK;
+    if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); *out = nullptr; return REDUX_CUDA_ERROR; }
+    return REDUX_OK;
+}
+extern "C" int redux_host_free(void *p)
+{
+    if (!p) return REDUX_OK;
+    if (cudaFreeHost(p) != cudaSuccess) { (void)cudaGetLastError(); return REDUX_CUDA_ERROR; }
+    return REDUX_OK;
+}
+extern "C" int redux_host_register(void *p, size_t bytes)
+{
+    if (!p || bytes == 0) return REDUX_INVALID_INPUT;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) { (void)cudaGetLastError(); return REDUX_CUDA_ERROR; }
+    return REDUX_OK;
+}
+extern "C" int redux_host_unregister(void *p)
+{
+    if (!p) return REDUX_INVALID_INPUT;
+    if (cudaHostUnregister(p) != cudaSuccess) { (void)cudaGetLastError(); return REDUX_CUDA_ERROR; }
+    return REDUX_OK;
+}
+
 // ======================================================================================= context
 
 extern "C" int redux_ctx_create(const int *devices, int n_devices, redux_ctx_t **out)
@@ -565,7 +619,8 @@ extern "C" int redux_ctx_create(const int *devices, int n_devices, redux_ctx_t *
         cudaDeviceProp prop;
         if (!g.ok || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { redux_ctx_destroy(ctx); return REDUX_CUDA_ERROR; }
         if (prop.major < 10) { redux_ctx_destroy(ctx); return REDUX_CUDA_ERROR; }   // sm_100a binary only
-        bool streams_ok = cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking) == cudaSuccess &&
+        bool streams_ok = cudaEventCreateWithFlags(&d.ws_busy, cudaEventDisableTiming) == cudaSuccess &&
+                          cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking) == cudaSuccess &&
                           cudaStreamCreateWithFlags(&d.h2d, cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < kPipeStreams && streams_ok; ++i)
             streams_ok = cudaStreamCreateWithFlags(&d.pipe[i], cudaStreamNonBlocking) == cudaSuccess;
@@ -590,6 +645,7 @@ extern "C" void redux_ctx_destroy(redux_ctx_t *ctx)
     for (auto &d : ctx->devs) {
         DeviceGuard g(d.device);
         cudaDeviceSynchronize();
+        if (d.ws_busy) cudaEventDestroy(d.ws_busy);
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.copy) cudaStreamDestroy(d.copy);
         if (d.h2d) cudaStreamDestroy(d.h2d);
@@ -761,15 +817,18 @@ extern "C" int redux_encode_batch_device(redux_ctx_t *ctx, int device, void *str
     if (n_blocks == 0) { CU_TRY(ctx, cudaMemsetAsync(d_out_offsets, 0, sizeof(uint64_t), s)); return REDUX_OK; }
     if (n_blocks > 0x7FFFFFFFull * 32) return fail(ctx, REDUX_UNSUPPORTED, "too many blocks in one launch");
 
+    CU_TRY(ctx, ws_acquire(d, s));              // the previous device call may still be using the workspace
     const void *magic = nullptr;
     if ((rc = get_magic(ctx, d, s, pl, &magic))) return rc;
     if ((rc = prepare_generic(ctx, d, s, params, n_blocks, &pl))) return rc;
     CU_TRY(ctx, d->slots.reserve(n_blocks * pl.slot_stride));
     CU_TRY(ctx, d->sizes.reserve(n_blocks * sizeof(uint32_t)));
     CU_TRY(ctx, d->flag.reserve(sizeof(int32_t)));
-    return encode_launch(ctx, device, s, pl, magic, d_in, d_in_offsets, n_blocks, d_out, out_capacity,
-                         d_out_offsets, d_status, (uint8_t *)d->slots.p, (uint32_t *)d->sizes.p,
-                         (int32_t *)d->flag.p);
+    rc = encode_launch(ctx, device, s, pl, magic, d_in, d_in_offsets, n_blocks, d_out, out_capacity,
+                       d_out_offsets, d_status, (uint8_t *)d->slots.p, (uint32_t *)d->sizes.p,
+                       (int32_t *)d->flag.p);
+    CU_TRY(ctx, ws_release(d, s));
+    return rc;
 }
 
 extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *stream_, int model_kind,
@@ -792,11 +851,14 @@ extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *str
         return fail(ctx, REDUX_INVALID_INPUT, "NULL buffer");
     DeviceGuard g(device);
     cudaStream_t s = (cudaStream_t)stream_;   // NULL = the default stream, as in CUDA
+    CU_TRY(ctx, ws_acquire(d, s));
     const void *magic = nullptr;
     if ((rc = get_magic(ctx, d, s, pl, &magic))) return rc;
     if ((rc = prepare_generic(ctx, d, s, params, n_blocks, &pl))) return rc;
-    return decode_launch(ctx, device, s, pl, magic, d_comp, d_comp_offsets, n_blocks, d_raw, d_raw_offsets,
-                         d_raw_lens, d_consumed, d_status);
+    rc = decode_launch(ctx, device, s, pl, magic, d_comp, d_comp_offsets, n_blocks, d_raw, d_raw_offsets,
+                       d_raw_lens, d_consumed, d_status);
+    CU_TRY(ctx, ws_release(d, s));
+    return rc;
 }
 
 extern "C" int redux_generate_blocks_device(redux_ctx_t *ctx, int device, void *stream_, uint8_t *d_out,
@@ -943,25 +1005,52 @@ void drain(DeviceState *d)
     cudaStreamSynchronize(d->copy);
 }
 
-// One device's shard of redux_encode_batch.
-//   stream_out != nullptr: the compacted bytes of chunk k are copied to stream_out + (bytes of the chunks
-//       before it) as soon as the chunk is done (single-device case: the shard's global base is known).
-//   stream_out == nullptr: the bytes stay on the device (st_out, chunk k at chunk_base[k]); the caller
-//       places them once the totals of the lower shards are known.
+// Cross-shard hand-off of redux_encode_batch on several devices.  The streams of the whole batch lie back to
+// back in the caller's buffer, so shard g's bytes start where the shards below it end: every worker publishes
+// its total as soon as its last chunk is coded, waits for the totals below it, and then copies its own bytes
+// out -- no worker waits for a shard ABOVE it, shard 0 streams chunk by chunk from the start.
+struct ShardSync {
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<int64_t> total;           // -1: not known yet
+    bool aborted = false;
+    explicit ShardSync(size_t n) : total(n, -1) {}
+    void publish(size_t g, uint64_t t) { { std::lock_guard<std::mutex> l(m); total[g] = (int64_t)t; } cv.notify_all(); }
+    void abort() { { std::lock_guard<std::mutex> l(m); aborted = true; } cv.notify_all(); }
+    // base offset of shard g; false when another shard failed
+    bool base_of(size_t g, uint64_t *base) {
+        std::unique_lock<std::mutex> l(m);
+        cv.wait(l, [&] {
+            if (aborted) return true;
+            for (size_t i = 0; i < g; ++i) if (total[i] < 0) return false;
+            return true;
+        });
+        if (aborted) return false;
+        uint64_t b = 0;
+        for (size_t i = 0; i < g; ++i) b += (uint64_t)total[i];
+        *base = b;
+        return true;
+    }
+};
+
+// One device's shard of redux_encode_batch: shard g of the hand-off `sync` (nullptr: the only shard).
+// Shard 0 knows its base (0) from the start and copies the compacted bytes of chunk k to out + (bytes of the
+// chunks before it) as soon as the chunk is done; a higher shard keeps its bytes on the device (st_out, chunk k
+// at chunk_base[k]) until the shards below it have published their totals.
 struct EncShardOut {
     std::vector<uint64_t> local_off;     // [count+1] shard-local offsets of the back-to-back streams
     std::vector<uint64_t> chunk_base;    // device offset of chunk k inside st_out
     std::vector<uint64_t> chunk_total;   // compacted bytes of chunk k
     std::vector<Shard> chunks;
     uint64_t total = 0;
-    bool overflow = false;               // stream_out only: capacity ran out
 };
 
 int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t *p, const uint8_t *in,
-                 const uint64_t *in_off, Shard sh, uint8_t *stream_out, uint64_t stream_cap,
-                 int32_t *status, EncShardOut *res)
+                 const uint64_t *in_off, Shard sh, uint8_t *out, uint64_t out_cap,
+                 int32_t *status, EncShardOut *res, ShardSync *sync, size_t g_index)
 {
     (void)kind;
+    const bool streaming = !sync || g_index == 0;          // the shard's base is known up front
     Trace tr;
     DeviceGuard g(d->device);
     const uint64_t base = in_off[sh.first], bytes = in_off[sh.first + sh.count] - base;
@@ -1045,6 +1134,14 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     tr.mark("encode: all chunks enqueued");
     // in order: offsets of chunk k become shard-local offsets; its bytes go out while later chunks run
     uint64_t pos = 0;
+    // copies the prefix of chunk k that fits the caller's buffer to out + at
+    auto place = [&](size_t k, uint64_t at) -> cudaError_t {
+        uint64_t nbytes = res->chunk_total[k];
+        if (at >= out_cap) return cudaSuccess;
+        if (at + nbytes > out_cap) nbytes = out_cap - at;
+        if (!nbytes) return cudaSuccess;
+        return cudaMemcpyAsync(out + at, d_out + res->chunk_base[k], nbytes, cudaMemcpyDeviceToHost, d->copy);
+    };
     for (size_t k = 0; k < nc; ++k) {
         const Shard c = res->chunks[k];
         cudaError_t e = cudaEventSynchronize(evs.ev[k]);
@@ -1054,17 +1151,24 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
         for (uint64_t i = 0; i <= c.count; ++i) res->local_off[c.first + i] = pos + lo[i];
         std::memcpy(status + c.first, h_status + c.first, c.count * sizeof(int32_t));
         res->chunk_total[k] = lo[c.count];
-        if (stream_out && !res->overflow) {
-            uint64_t nbytes = lo[c.count];
-            if (pos + nbytes > stream_cap) { res->overflow = true; nbytes = stream_cap - pos; }   // the prefix that fits
-            if (nbytes) {
-                e = cudaMemcpyAsync(stream_out + pos, d_out + res->chunk_base[k], nbytes, cudaMemcpyDeviceToHost, d->copy);
-                if (e != cudaSuccess) { drain(d); (void)cudaGetLastError(); return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline D2H", e); }
-            }
+        if (streaming && (e = place(k, pos)) != cudaSuccess) {
+            drain(d); (void)cudaGetLastError();
+            return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline D2H", e);
         }
         pos += lo[c.count];
     }
     res->total = pos;
+    if (sync) sync->publish(g_index, pos);
+    if (!streaming) {
+        uint64_t at = 0;
+        if (!sync->base_of(g_index, &at)) { drain(d); return REDUX_OK; }     // another shard failed: its code is the call's
+        tr.mark("encode: base known");
+        for (size_t k = 0; k < nc; ++k) {
+            cudaError_t e = place(k, at);
+            if (e != cudaSuccess) { drain(d); (void)cudaGetLastError(); return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline D2H", e); }
+            at += res->chunk_total[k];
+        }
+    }
     CU_TRY(ctx, cudaStreamSynchronize(d->copy));
     tr.mark("encode: last D2H done");
     return REDUX_OK;
@@ -1089,17 +1193,18 @@ extern "C" int redux_encode_batch(redux_ctx_t *ctx, int model_kind, const redux_
     std::vector<Shard> shards = make_shards(n_blocks, nd);
     std::vector<EncShardOut> res(nd);
     std::vector<int> rcs(nd, REDUX_OK);
+    ShardSync sync(nd);
     for_each_device(ctx, nd, rcs, [&](redux_ctx *view, DeviceState *d, size_t g) {
-        return encode_shard(view, d, model_kind, params, in, in_offsets, shards[g],
-                            nd == 1 ? out : nullptr, out_capacity, status + shards[g].first, &res[g]);
+        const int r = encode_shard(view, d, model_kind, params, in, in_offsets, shards[g], out, out_capacity,
+                                   status + shards[g].first, &res[g], nd > 1 ? &sync : nullptr, g);
+        if (r != REDUX_OK) sync.abort();
+        return r;
     });
     for (size_t g = 0; g < nd; ++g) if (rcs[g]) return rcs[g];
 
-    // global offsets; with several devices the bytes are placed now that every shard's base is known
+    // global offsets (the bytes are already in place: every shard copied its own)
     uint64_t base = 0;
-    std::vector<uint64_t> bases(nd);
     for (size_t g = 0; g < nd; ++g) {
-        bases[g] = base;
         for (uint64_t i = 0; i <= shards[g].count; ++i) out_offsets[shards[g].first + i] = base + res[g].local_off[i];
         base += res[g].total;
     }
@@ -1107,23 +1212,6 @@ extern "C" int redux_encode_batch(redux_ctx_t *ctx, int model_kind, const redux_
         for (uint64_t i = 0; i < n_blocks; ++i)
             if (out_offsets[i + 1] > out_capacity) status[i] = REDUX_OUT_CAPACITY;
         return fail(ctx, REDUX_OUT_CAPACITY, "output buffer too small for the compressed batch");
-    }
-    if (nd > 1) {
-        for (size_t g = 0; g < nd; ++g) {
-            DeviceState &d = ctx->devs[g];
-            DeviceGuard gd(d.device);
-            uint64_t pos = bases[g];
-            for (size_t k = 0; k < res[g].chunks.size(); ++k) {
-                if (res[g].chunk_total[k])
-                    CU_TRY(ctx, cudaMemcpyAsync(out + pos, (const uint8_t *)d.st_out.p + res[g].chunk_base[k],
-                                                res[g].chunk_total[k], cudaMemcpyDeviceToHost, d.copy));
-                pos += res[g].chunk_total[k];
-            }
-        }
-        for (size_t g = 0; g < nd; ++g) {
-            DeviceGuard gd(ctx->devs[g].device);
-            CU_TRY(ctx, cudaStreamSynchronize(ctx->devs[g].copy));
-        }
     }
     for (uint64_t i = 0; i < n_blocks; ++i) if (status[i]) return status[i];
     return REDUX_OK;
@@ -1304,6 +1392,34 @@ extern "C" int redux_decode_batch_ex(redux_ctx_t *ctx, int model_kind, const red
     ctx->model_freq = model_freq;
     const int rc = redux_decode_batch(ctx, model_kind, params, comp, comp_offsets, n_blocks, raw, raw_offsets,
                                       raw_lens, consumed, status);
+    ctx->model_freq = nullptr;
+    return rc;
+}
+
+extern "C" int redux_encode_batch_device_ex(redux_ctx_t *ctx, int device, void *stream, int model_kind,
+                                            const redux_params_t *params, const uint32_t *model_freq,
+                                            const uint8_t *d_in, const uint64_t *d_in_offsets, uint64_t n_blocks,
+                                            uint64_t max_block_len, uint8_t *d_out, uint64_t out_capacity,
+                                            uint64_t *d_out_offsets, int32_t *d_status)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    ctx->model_freq = model_freq;               // HOST pointer; uploaded and turned into the start tree on `stream`
+    const int rc = redux_encode_batch_device(ctx, device, stream, model_kind, params, d_in, d_in_offsets, n_blocks,
+                                             max_block_len, d_out, out_capacity, d_out_offsets, d_status);
+    ctx->model_freq = nullptr;
+    return rc;
+}
+
+extern "C" int redux_decode_batch_device_ex(redux_ctx_t *ctx, int device, void *stream, int model_kind,
+                                            const redux_params_t *params, const uint32_t *model_freq,
+                                            const uint8_t *d_comp, const uint64_t *d_comp_offsets, uint64_t n_blocks,
+                                            uint64_t max_block_len, uint8_t *d_raw, const uint64_t *d_raw_offsets,
+                                            uint64_t *d_raw_lens, uint64_t *d_consumed, int32_t *d_status)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    ctx->model_freq = model_freq;
+    const int rc = redux_decode_batch_device(ctx, device, stream, model_kind, params, d_comp, d_comp_offsets, n_blocks,
+                                             max_block_len, d_raw, d_raw_offsets, d_raw_lens, d_consumed, d_status);
     ctx->model_freq = nullptr;
     return rc;
 }
