@@ -117,6 +117,10 @@ int oracle_decompress_batch(int kind, uint64_t s, uint64_t f, uint64_t c,
                             uint8_t *out, const uint64_t *out_off, uint64_t *out_len,
                             uint64_t *consumed, int32_t *status, int n_threads);
 
+/* synth_blocks.c: the synthetic mixed-entropy blocks of BASELINE.json configs 3-4 (block index & 3: uniform /
+ * text-like / geometric / sparse), n_blocks blocks of block_len bytes starting at block index first_block. */
+void oracle_generate_blocks(uint8_t *out, uint64_t first_block, uint64_t n_blocks, uint64_t block_len, uint64_t seed);
+
 #ifdef __cplusplus
 }
 #endif

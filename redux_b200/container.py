@@ -43,6 +43,14 @@ def read_header(f):
 def pack_stream(fin, fout, model, block_len=65536, batch_blocks=16384, context=None):
     """Reads fin to the end, codes it in batches of `batch_blocks` blocks, writes the container to fout.
     Returns (raw_bytes, container_bytes)."""
+    # The header records the model KIND and Parameters only, and unpack_stream() rebuilds a fresh model from it: a
+    # model trained before the call would produce streams nothing in the file says how to decode.  Likewise the
+    # segment index stores whole bytes per block: with symbol_bits != 8 the reference drops a trailing partial
+    # symbol (src/bitio/mod.rs:94-108), so decoded lengths would not match.  Refuse both at pack time.
+    if model.freq is not None:
+        raise ContainerError("the container stores fresh models only (a trained model is not recorded in the header)")
+    if model.params.symbol_bits != 8:
+        raise ContainerError("the container stores byte-symbol streams only (symbol_bits must be 8)")
     ctx = context or rb._ctx()
     write_header(fout, model, block_len)
     raw_total, out_total = 0, HEADER.size

@@ -583,30 +583,27 @@ struct LaneDecoderAl {
                 const uint32_t ar = cached ? top_a : (uint32_t)p[m << 5];
                 const uint32_t br = cached ? top_b : (uint32_t)p[(h << 5) + oddadj];
                 const uint32_t cr = cached ? top_c : (uint32_t)p[((m + h) << 5) + oddadj];
-                const uint32_t a = (FULL ? 0u : (uint32_t)m) + ar;
-                const uint32_t b = (FULL ? 0u : (uint32_t)h) + br;
-                const uint32_t cc = (FULL ? 0u : (uint32_t)h) + cr;
-                const P pa = C::mul_add(a, rm1, plo);
-                const P pb = C::mul_add(b, rm1, plo);
-                const P pc = C::mul_add(cc, rm1, pa);
-                const bool ra = X >= pa, rb = X >= pb, rc = X >= pc;
-                const bool r2 = ra ? rc : rb;                                   // second-level decision
+                const P pa = C::mul_add((FULL ? 0u : (uint32_t)m) + ar, rm1, plo);
+                const P pb = C::mul_add((FULL ? 0u : (uint32_t)h) + br, rm1, plo);
+                const P pc = C::mul_add((FULL ? 0u : (uint32_t)h) + cr, rm1, pa);
+                const bool ra = X >= pa;                                        // first-level decision
                 const P p2 = ra ? pc : pb;                                      // second-level boundary
-                const P base = ra ? pa : plo;
+                const bool r2 = X >= p2;                                        // second-level decision
+                TW *pm = p + (ra ? (m << 5) : 0);                               // row of the node the second level starts from
                 if (UPD) {
+                    // a left turn = the node covers the symbol from above = it is on the symbol's update path
+                    const uint32_t v2 = (ra ? cr : br) + 1u;
                     if (cached) {
-                        top_a += ra ? 0u : 1u;
-                        top_b += (!ra && !rb) ? 1u : 0u;
-                        top_c += (ra && !rc) ? 1u : 0u;
+                        if (!ra) top_a += 1u;
+                        if (!r2) { if (ra) top_c = v2; else top_b = v2; }
                     } else {
                         if (!ra) p[m << 5] = (TW)(ar + 1u);
-                        if (ra && !rc) p[((m + h) << 5) + oddadj] = (TW)(cr + 1u);
-                        if (!ra && !rb) p[(h << 5) + oddadj] = (TW)(br + 1u);
+                        if (!r2) pm[(h << 5) + oddadj] = (TW)v2;
                     }
                 }
                 phi = r2 ? (ra ? phi : pa) : p2;
-                plo = r2 ? p2 : base;
-                p += (ra ? (m << 5) : 0) + (r2 ? (h << 5) : 0);
+                plo = r2 ? p2 : (ra ? pa : plo);
+                p = pm + (r2 ? (h << 5) : 0);
             }
         } else if (count > kQuotientMaxCount) {
             // 64-bit products, very long streams: the plain product-domain descent
@@ -653,24 +650,23 @@ struct LaneDecoderAl {
                 const uint32_t a = lo + (FULL ? 0u : (uint32_t)m) + ar;
                 const uint32_t b = lo + (FULL ? 0u : (uint32_t)h) + br;
                 const uint32_t cc = a + (FULL ? 0u : (uint32_t)h) + cr;
-                const bool ra = v >= a, rb = v >= b, rc = v >= cc;
-                const bool r2 = ra ? rc : rb;
+                const bool ra = v >= a;
                 const uint32_t p2 = ra ? cc : b;
-                const uint32_t base = ra ? a : lo;
+                const bool r2 = v >= p2;
+                TW *pm = p + (ra ? (m << 5) : 0);
                 if (UPD) {
+                    const uint32_t v2 = (ra ? cr : br) + 1u;
                     if (cached) {
-                        top_a += ra ? 0u : 1u;
-                        top_b += (!ra && !rb) ? 1u : 0u;
-                        top_c += (ra && !rc) ? 1u : 0u;
+                        if (!ra) top_a += 1u;
+                        if (!r2) { if (ra) top_c = v2; else top_b = v2; }
                     } else {
                         if (!ra) p[m << 5] = (TW)(ar + 1u);
-                        if (ra && !rc) p[((m + h) << 5) + oddadj] = (TW)(cr + 1u);
-                        if (!ra && !rb) p[(h << 5) + oddadj] = (TW)(br + 1u);
+                        if (!r2) pm[(h << 5) + oddadj] = (TW)v2;
                     }
                 }
                 hi = r2 ? (ra ? hi : a) : p2;
-                lo = r2 ? p2 : base;
-                p += (ra ? (m << 5) : 0) + (r2 ? (h << 5) : 0);
+                lo = r2 ? p2 : (ra ? a : lo);
+                p = pm + (r2 ? (h << 5) : 0);
             }
             plo = C::mulr(lo, rm1);
             phi = C::mulr(hi, rm1);

@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
 _SO = os.path.join(ORACLE_DIR, "libredux_oracle.so")
+_SO_NATIVE = os.path.join(ORACLE_DIR, "libredux_oracle_native.so")
 
 OK, EOF, INVALID_INPUT, IO_ERROR = 0, 1, 2, 3
 LINEAR, TREE = 0, 1
@@ -24,22 +25,43 @@ class Params(C.Structure):
 
 
 def build(force=False):
-    src = os.path.join(ORACLE_DIR, "redux_oracle.c")
-    if force or not os.path.exists(_SO) or (
-            os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_SO)):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("redux_oracle.c", "synth_blocks.c", "redux_oracle.h")]
+    if force or not os.path.exists(_SO) or any(
+            os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_SO) for src in srcs):
         subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
     return _SO
 
 
 _lib = None
+_flavour = "portable (-O3)"
+
+
+def use_native_build():
+    """bench.py's CPU arm: rebuild the oracle with -O3 -march=native ON THIS HOST and load that build (must be
+    called before the first lib()).  Falls back to the portable build when there is no compiler.  Returns a
+    description for the JSON line."""
+    global _SO, _flavour
+    if _lib is not None:
+        return _flavour
+    try:
+        r = subprocess.run(["make", "-C", ORACLE_DIR, "-s", "-B", "native"], capture_output=True, text=True, timeout=120)
+        if r.returncode == 0 and os.path.exists(_SO_NATIVE):
+            _SO = _SO_NATIVE
+            _flavour = "-O3 -march=native, built on this host"
+    except Exception:
+        pass
+    return _flavour
 
 
 def lib():
     global _lib
     if _lib is not None:
         return _lib
-    build()
+    if _SO != _SO_NATIVE:
+        build()
     L = C.CDLL(_SO)
+    L.oracle_generate_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.oracle_generate_blocks.restype = None
     u64, p8, pu64 = C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)
     L.oracle_params_new.argtypes = [u64, u64, u64, C.POINTER(Params)]
     L.oracle_params_new.restype = C.c_int
@@ -151,6 +173,13 @@ def trained_frequencies(train, kind=TREE, params=(8, 30, 32)):
         assert rc == OK
     tab = m.get_freq_table()
     return (tab[:, 1] - tab[:, 0]).astype(np.uint32)
+
+
+def generate_blocks(first_block, n_blocks, block_len, seed):
+    """The synthetic mixed-entropy blocks of the benchmark, from the oracle side (oracle/synth_blocks.c)."""
+    out = np.empty(n_blocks * block_len, dtype=np.uint8)
+    lib().oracle_generate_blocks(out.ctypes.data, first_block, n_blocks, block_len, seed)
+    return out
 
 
 def compress_batch(inp, in_off, kind=TREE, params=(8, 30, 32), threads=1):

@@ -47,3 +47,29 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     ours = _load("r01_final5_bench_default.json")
     assert d["metric"] == ours["metric"] and d["config"]["workload"] == ours["config"]["workload"]
+
+
+def test_reference_arm_runs_without_mapping_the_product_library():
+    """The CPU arm generates its input with oracle/synth_blocks.c and codes with oracle/redux_oracle.c: after a
+    run, /proc/self/maps of that process holds the oracle library and not libredux_b200.so."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, io, json, contextlib\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--cpu-sample-blocks', '8']\n"
+        "sys.path.insert(0, %r)\n"
+        "import bench\n"
+        "buf = io.StringIO()\n"
+        "with contextlib.redirect_stdout(buf):\n"
+        "    bench.run_reference(bench.parse_args())\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "d = json.loads(buf.getvalue())\n"
+        "print(json.dumps({'oracle': 'libredux_oracle' in maps, 'product': 'libredux_b200' in maps, 'line': d}))\n"
+    ) % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["oracle"] and not out["product"]
+    line = out["line"]
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["cpu_baseline"]["per_thread_MBps"] > 0 and line["cpu_baseline"]["MiBps"] > 0

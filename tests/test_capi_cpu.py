@@ -203,3 +203,12 @@ def test_product_package_does_not_touch_oracle():
     syms = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "redux_b200", "libredux_b200.so")],
                           capture_output=True, text=True).stdout
     assert "emu_" not in syms and "oracle_" not in syms
+
+
+def test_oracle_side_generator_equals_the_products_host_generator():
+    """bench.py's CPU arm generates its input with oracle/synth_blocks.c so that it never maps the product
+    library; the bytes must be the ones the product's generator (and therefore the GPU) produces."""
+    import oracle_lib as o
+    seed = 0x5EED202610180000
+    for first, n, L in ((0, 64, 4096), (5, 9, 1001), (65530, 8, 65536), (3, 4, 7)):
+        assert (o.generate_blocks(first, n, L, seed) == rb.generate_blocks_host(first, n, L, seed)).all()

@@ -51,3 +51,13 @@ def test_container_roundtrip_and_block_parity():
     with pytest.raises(rb.Eof):
         ct.unpack(blob[: len(blob) // 2])
     assert ct.unpack(ct.pack(b"", model)) == b""
+
+
+def test_pack_refuses_what_the_header_cannot_describe():
+    """A trained model or a symbol width other than 8 would write a container unpack_stream() cannot decode (the
+    header holds kind + Parameters only; the index holds whole bytes): rejected when packing, before any device call."""
+    trained = rb.AdaptiveTreeModel(rb.Parameters(8, 14, 16)).train([1, 2, 3])
+    with pytest.raises(ct.ContainerError):
+        ct.pack(b"abc", trained)
+    with pytest.raises(ct.ContainerError):
+        ct.pack(b"abc", rb.AdaptiveTreeModel(rb.Parameters(12, 14, 16)))
