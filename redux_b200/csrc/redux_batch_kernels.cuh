@@ -15,7 +15,8 @@ template <> struct MagicMaker<Magic32> {
     static __device__ Magic32 make(uint32_t d, uint32_t nbits) { return make_magic32(d, nbits); }
 };
 template <> struct MagicMaker<Magic64> {
-    static __device__ Magic64 make(uint32_t d, uint32_t nbits) { return make_magic64(d, nbits); }
+    // nbits == 0: the 65-bit scheme of the HUGE class (any 64-bit numerator)
+    static __device__ Magic64 make(uint32_t d, uint32_t nbits) { return nbits ? make_magic64(d, nbits) : make_magic65(d); }
 };
 
 // out[tt] = magic of count 257 + tt for numerators < 2^nbits

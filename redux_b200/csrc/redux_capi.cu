@@ -163,6 +163,9 @@ cudaError_t configure_kernels()
     RDX_CFG((encode_lane_al_kernel<uint32_t, kWide, true, C32>), s32)  RDX_CFG((decode_lane_al_kernel<uint32_t, kWide, true, C32, false>), s32)
     RDX_CFG_WIDE(false) RDX_CFG_WIDE(true)
 #undef RDX_CFG_WIDE
+    // generic kernels: Fenwick columns of alphabets up to 7 bits in shared memory (66 KB per CTA at 7 bits)
+    RDX_CFG(encode_generic_kernel, generic_smem_bytes(kGenericSmemSymbolBits))
+    RDX_CFG(decode_generic_kernel, generic_smem_bytes(kGenericSmemSymbolBits))
 #undef RDX_CFG
     return cudaSuccess;
 }
@@ -254,8 +257,8 @@ int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, P
 int get_magic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const Plan &pl, const void **out)
 {
     *out = nullptr;
-    if (pl.cls == kHuge || pl.generic) return REDUX_OK;
-    const uint32_t nbits = pl.f + pl.c;
+    if (pl.generic) return REDUX_OK;
+    const uint32_t nbits = pl.cls == kHuge ? 0u : pl.f + pl.c;      // HUGE: one table serves every numerator width
     for (auto &m : d->magics)
         if (m.cls == pl.cls && m.nbits == nbits && m.len >= pl.magic_len) { *out = m.ptr; return REDUX_OK; }
     const size_t esz = pl.cls == kNarrow ? sizeof(Magic32) : sizeof(Magic64);
@@ -503,6 +506,7 @@ extern "C" uint64_t redux_compress_bound_ex(uint64_t in_len, uint32_t symbol_bit
 extern "C" int redux_debug_magic(uint64_t d, uint32_t nbits, int wide, uint64_t *magic, uint32_t *shift)
 {
     if (d < 1 || d >> 32) return REDUX_INVALID_INPUT;
+    if (wide == 2) { if (d < 2) return REDUX_INVALID_INPUT; Magic64 g = make_magic65(d); *magic = g.m; *shift = g.sh; return REDUX_OK; }
     if (wide) { if (nbits > 62) return REDUX_INVALID_INPUT; Magic64 g = make_magic64(d, nbits); *magic = g.m; *shift = g.sh; }
     else      { if (nbits > 30) return REDUX_INVALID_INPUT; Magic32 g = make_magic32((uint32_t)d, nbits); *magic = g.m; *shift = g.sh; }
     return REDUX_OK;
@@ -510,6 +514,7 @@ extern "C" int redux_debug_magic(uint64_t d, uint32_t nbits, int wide, uint64_t 
 
 extern "C" uint64_t redux_debug_magic_divide(uint64_t n, uint64_t magic, uint32_t shift, int wide)
 {
+    if (wide == 2) { Magic64 g{magic, shift, 0}; return div_magic65(n, g); }
     if (wide) { Magic64 g{magic, shift, 0}; return div_magic64(n, g); }
     Magic32 g{(uint32_t)magic, shift};
     return div_magic32((uint32_t)n, g);
@@ -730,7 +735,7 @@ int encode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
             GenericJob g = generic_job(pl);
             g.in = d_in; g.in_off = d_in_off; g.n_blocks = n_blocks;
             g.slots = slots; g.slot_stride = pl.slot_stride; g.sizes = sizes; g.status = d_status;
-            encode_generic_kernel<<<pl.gen_threads / kGenericThreads, kGenericThreads, 0, s>>>(g);
+            encode_generic_kernel<<<pl.gen_threads / kGenericThreads, kGenericThreads, generic_smem_bytes(pl.s), s>>>(g);
         }
         else if (pl.split) {
             DeviceState *d = find_dev(ctx, device);
@@ -781,7 +786,7 @@ int decode_launch(redux_ctx *ctx, int device, cudaStream_t s, const Plan &pl, co
             GenericJob g = generic_job(pl);
             g.in = d_comp; g.in_off = d_comp_off; g.n_blocks = n_blocks;
             g.raw = d_raw; g.raw_off = d_raw_off; g.raw_len = d_raw_lens; g.consumed = d_consumed; g.status = d_status;
-            decode_generic_kernel<<<pl.gen_threads / kGenericThreads, kGenericThreads, 0, s>>>(g);
+            decode_generic_kernel<<<pl.gen_threads / kGenericThreads, kGenericThreads, generic_smem_bytes(pl.s), s>>>(g);
         }
         else if (pl.warp)       launch_decode_warp(pl.cls, job, s);
         else if (pl.aligned)    launch_decode_al(pl, job, grid, smem, s);

@@ -97,6 +97,21 @@ RDX_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 RDX_HD uint32_t div_magic32(uint32_t n, Magic32 g) { return mulhi32(n, g.m) >> g.sh; }
 RDX_HD uint64_t div_magic64(uint64_t n, Magic64 g) { return mulhi64(n, g.m) >> g.sh; }
 
+// code_bits > 32: numerators reach 2^64 (code + freq <= 64, src/model/mod.rs:64), one bit more than a 64-bit magic can
+// serve.  The 65-bit magic 2^64 + m' of p = 64 + l, l = ceil(log2 d), divides EVERY 64-bit numerator exactly
+// (e = (2^64 + m') d - 2^p lies in [1, d] and n e < 2^64 2^l = 2^p); its product with n is formed without the carry:
+// t = mulhi(n, m') <= n, (n + t) / 2 = ((n - t) >> 1) + t, then the remaining l - 1 bits of the shift (l >= 9 here:
+// d >= 257).  Two of these replace the two 64-bit hardware-less divisions per symbol the HUGE class used to pay.
+RDX_HD Magic64 make_magic65(uint64_t d) {
+    const uint32_t l = ceil_log2_u64(d);
+    Magic64 r; r.m = pow2_div(64 + l, d) + 1; r.sh = l; r.pad = 0;     // pow2_div truncates to 64 bits: drops the 2^64
+    return r;
+}
+RDX_HD uint64_t div_magic65(uint64_t n, Magic64 g) {
+    const uint64_t t = mulhi64(n, g.m);
+    return (((n - t) >> 1) + t) >> (g.sh - 1);
+}
+
 RDX_HD int clz32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
     return __clz((int)x);

@@ -16,9 +16,11 @@
 //     (src/model/mod.rs:23-25); its state is exactly the per-symbol frequency vector, handed over here
 //     as the Fenwick tree built from it.
 // The frequency table is the reference's tree itself (adaptive_tree.rs:34-136: u32 nodes, index 0 unused,
-// nodes 1..symbol_count) in GLOBAL memory, one column per thread of the grid ([node][thread], so the
-// per-block reset is coalesced); a thread codes blocks tid, tid + T, ... with the same column.  This is
-// the completeness path: L2-latency bound, no reciprocal tables, loops as the reference writes them.
+// nodes 1..symbol_count), one column per thread: [node][thread], so that the 32 data-dependent walks of a
+// warp touch 32 different banks / one coalesced row.  Alphabets of up to 7 bits (130 nodes, 66 KB per CTA)
+// keep their columns in SHARED memory; wider ones in GLOBAL memory (L2-latency bound), where a thread codes
+// blocks tid, tid + T, ... with the same column.  This is the completeness path: no reciprocal tables, loops
+// as the reference writes them.
 #pragma once
 #include "redux_common.cuh"
 #include "redux_lane_codec.cuh"
@@ -27,6 +29,11 @@ namespace rdx {
 
 constexpr uint32_t kGenericMaxSymbolBits = 16;
 constexpr int kGenericThreads = 128;
+constexpr uint32_t kGenericSmemSymbolBits = 7;      // up to this width the Fenwick columns live in shared memory
+// dynamic shared memory of the generic kernels: [nsym + 1][kGenericThreads] u32, or nothing
+RDX_HD size_t generic_smem_bytes(uint32_t s) {
+    return s <= kGenericSmemSymbolBits ? ((size_t)(1u << s) + 2) * kGenericThreads * sizeof(uint32_t) : 0;
+}
 
 struct GenericJob {
     const uint8_t *in;          // encode: raw bytes / decode: compressed bytes
@@ -49,8 +56,9 @@ struct GenericTree {
     uint32_t *t; uint32_t stride;       // node i at t[i * stride]
     uint32_t nsym, eof, total, fmax;
 
-    __device__ __forceinline__ void reset(const GenericJob &job, uint32_t tid) {
-        t = job.tabs + tid; stride = job.n_threads;
+    __device__ __forceinline__ void reset(const GenericJob &job, uint32_t tid, uint32_t *smem_cols) {
+        if (job.s <= kGenericSmemSymbolBits) { t = smem_cols + threadIdx.x; stride = kGenericThreads; }
+        else                                 { t = job.tabs + tid; stride = job.n_threads; }
         eof = 1u << job.s; nsym = eof + 1;
         fmax = (uint32_t)(((uint64_t)1 << job.f) - 1);
         total = job.init_total;
@@ -98,6 +106,7 @@ struct SymbolSink {
 __global__ void __launch_bounds__(kGenericThreads)
 encode_generic_kernel(const GenericJob job)
 {
+    extern __shared__ uint32_t gen_cols[];
     const uint32_t tid = blockIdx.x * kGenericThreads + threadIdx.x;
     if (tid >= job.n_threads) return;
     const uint32_t c = job.c, s = job.s;
@@ -107,7 +116,7 @@ encode_generic_kernel(const GenericJob job)
         const uint64_t off = job.in_off[blk];
         const uint64_t len = job.in_off[blk + 1] - off;
         if (len >= (1ull << 29)) { job.sizes[blk] = 0; job.status[blk] = 5; continue; }
-        tree.reset(job, tid);
+        tree.reset(job, tid, gen_cols);
         BitSource src;                                       // read_bits(symbol_bits) over the raw bytes
         src.init(job.in + off, (uint32_t)len);
         BitSink sink;
@@ -142,6 +151,7 @@ encode_generic_kernel(const GenericJob job)
 __global__ void __launch_bounds__(kGenericThreads)
 decode_generic_kernel(const GenericJob job)
 {
+    extern __shared__ uint32_t gen_cols[];
     const uint32_t tid = blockIdx.x * kGenericThreads + threadIdx.x;
     if (tid >= job.n_threads) return;
     const uint32_t c = job.c, s = job.s;
@@ -153,7 +163,7 @@ decode_generic_kernel(const GenericJob job)
         const uint64_t clen = job.in_off[blk + 1] - coff;
         const uint64_t roff = job.raw_off[blk];
         if (clen >= (1ull << 29)) { job.raw_len[blk] = 0; job.consumed[blk] = 0; job.status[blk] = 5; continue; }
-        tree.reset(job, tid);
+        tree.reset(job, tid, gen_cols);
         BitSource src;
         src.init(job.in + coff, (uint32_t)clen);
         SymbolSink out;

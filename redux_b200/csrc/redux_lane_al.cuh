@@ -671,20 +671,23 @@ struct LaneDecoderAl {
             plo = C::mulr(lo, rm1);
             phi = C::mulr(hi, rm1);
         }
-        if (is_eof) {                                         // src/codec.rs:136-138: no renorm, no reads
-            st = -1;
-            return false;
-        }
         const uint32_t sym = (uint32_t)(p - tab.t) >> 5;
-        // src/codec.rs:133-134
+        // src/codec.rs:133-134 (for the EOF symbol the descent's products are meaningless but harmless: the step
+        // leaves through the single exit below before anything is stored or consumed)
         const uint32_t nh2 = ~((uint32_t)C::divc(phi, g, count) * one + (L - 1u));
         const uint32_t l2 = (uint32_t)C::divc(plo, g, count) * one + L;
         // src/codec.rs:140-158 in closed form
         const uint32_t n1 = common_prefix<C32>(~(l2 ^ nh2));
         const uint32_t k = clz_nz(~shl_c((l2 & nh2) << 1, n1));
         const uint32_t n = n1 + k;
-        if (n > left) { st = 1; left = 0; return false; }     // Err(Eof) inside get_bit (:49-52)
-        if (PEEK) { st = 6; return false; }                   // a data symbol with nowhere to go
+        // ONE exit per step: the EOF symbol (src/codec.rs:136-138: no renorm, no reads), bits running out inside
+        // get_bit (:49-52: Err(Eof)) or, when PEEK, a data symbol with nowhere to go
+        if ((int)PEEK | (int)is_eof | (int)(n > left)) {            // bitwise: one condition, one branch
+            if (is_eof) st = -1;
+            else if (n > left) { st = 1; left = 0; }
+            else st = 6;
+            return false;
+        }
         left -= n;
         // E1/E2: shift the window, pulling the next stream bits in; E3: keep the MSB, drop k bits below it
         const uint32_t win = bw.win();

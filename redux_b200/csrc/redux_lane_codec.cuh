@@ -105,9 +105,12 @@ template <> struct Cls<kHuge> {
     using S = uint64_t; using P = uint64_t; using M = Magic64;
     static __device__ __forceinline__ P mulr(uint32_t v, S rm1) { return (uint64_t)v * rm1 + v; }
     static __device__ __forceinline__ P mul_add(uint32_t v, S rm1, P acc) { return (uint64_t)v * (rm1 + 1u) + acc; }
-    static __device__ __forceinline__ P divc(P n, const M &, uint32_t count) { return n / count; }
-    static __device__ __forceinline__ M ldm(const M *) { M g; g.m = 0; g.sh = 0; g.pad = 0; return g; }
-    static __device__ __forceinline__ M mk(uint64_t, uint32_t) { M g; g.m = 0; g.sh = 0; g.pad = 0; return g; }
+    static __device__ __forceinline__ P divc(P n, const M &g, uint32_t) { return div_magic65(n, g); }
+    static __device__ __forceinline__ M ldm(const M *p) {
+        uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+        M g; g.m = ((uint64_t)v.y << 32) | v.x; g.sh = v.z; g.pad = 0; return g;
+    }
+    static __device__ __forceinline__ M mk(uint64_t m, uint32_t sh) { M g; g.m = m; g.sh = sh; g.pad = 0; return g; }
 };
 
 // ------------------------------------------------------------------ Fenwick increments in smem

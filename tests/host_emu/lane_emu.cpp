@@ -16,6 +16,11 @@ namespace rdx {
 uint4 smem_u4[(kLaneWarpsPerCta * kTabNodes * 32 * 4 + kTabPadBytes) / 16];
 }
 
+namespace rdx {
+// dynamic shared memory of the generic kernels: Fenwick columns of alphabets up to kGenericSmemSymbolBits
+uint32_t gen_cols[((1u << kGenericSmemSymbolBits) + 2) * kGenericThreads];
+}
+
 using namespace rdx;
 
 namespace {
@@ -23,8 +28,13 @@ namespace {
 std::vector<uint8_t> build_magic(const LanePlan &pl)
 {
     std::vector<uint8_t> buf;
-    if (pl.cls == kHuge) return buf;
     const uint32_t nbits = pl.f + pl.c;
+    if (pl.cls == kHuge) {
+        buf.resize(sizeof(Magic64) * pl.magic_len);
+        Magic64 *m = reinterpret_cast<Magic64 *>(buf.data());
+        for (uint32_t i = 0; i < pl.magic_len; ++i) m[i] = make_magic65(kNsym + i);
+        return buf;
+    }
     if (pl.cls == kNarrow) {
         buf.resize(sizeof(Magic32) * pl.magic_len);
         Magic32 *m = reinterpret_cast<Magic32 *>(buf.data());

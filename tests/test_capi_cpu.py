@@ -96,6 +96,25 @@ def test_count_reciprocal_is_exact(nbits, wide):
                 assert L.redux_debug_magic_divide(n, m, sh, wide) == n // d, (n, d, nbits)
 
 
+def test_count_reciprocal_65_bit_is_exact_for_every_64_bit_numerator():
+    """code_bits > 32: numerators reach 2^64 - 1 (code + freq <= 64), so the magic is 2^64 + m' and the product is
+    formed without the carry.  Exact for counts up to freq_max (2^31 - 1) and adversarial 64-bit numerators."""
+    rng = np.random.default_rng(65)
+    L = rb.lib()
+    top = (1 << 64) - 1
+    ds = [257, 258, 511, 512, 513, 65535, 65536, 65537, (1 << 20) + 1, (1 << 31) - 1, (1 << 31) - 2, 1 << 30]
+    ds += [int(x) for x in rng.integers(257, 1 << 31, size=80)]
+    for d in ds:
+        m, sh = _magic(d, 0, 2)
+        assert m < (1 << 64) and sh >= 9
+        ns = [0, 1, d - 1, d, d + 1, top, top - 1, (top // d) * d, (top // d) * d - 1, 1 << 63, (1 << 63) - 1]
+        ns += [int(x) for x in rng.integers(0, top, size=200, dtype=np.uint64)]
+        ks = [int(x) for x in rng.integers(1, top // d, size=100, dtype=np.uint64)]
+        ns += [k * d - 1 for k in ks] + [k * d for k in ks]
+        for n in ns:
+            assert L.redux_debug_magic_divide(int(n), m, sh, 2) == int(n) // d, (n, d)
+
+
 def test_count_reciprocal_exhaustive_small():
     """All numerators for a small class: nbits=18 over d in [257, 1023]."""
     for d in range(257, 1024, 7):
