@@ -33,6 +33,11 @@ extern "C" {
     pub fn redux_error_string(code: c_int) -> *const c_char;
     pub fn redux_compress_bound(in_len: u64, code_bits: u32) -> u64;
     pub fn redux_compress_bound_ex(in_len: u64, symbol_bits: u32, code_bits: u32) -> u64;
+    pub fn redux_process_init() -> c_int;
+    pub fn redux_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn redux_host_free(p: *mut c_void) -> c_int;
+    pub fn redux_host_register(p: *mut c_void, bytes: usize) -> c_int;
+    pub fn redux_host_unregister(p: *mut c_void) -> c_int;
     pub fn redux_ctx_create(devices: *const c_int, n_devices: c_int, ctx: *mut *mut redux_ctx_t) -> c_int;
     pub fn redux_ctx_destroy(ctx: *mut redux_ctx_t);
     pub fn redux_ctx_device_count(ctx: *const redux_ctx_t) -> c_int;

@@ -1,7 +1,8 @@
-"""Latency-bound configurations (BASELINE.json configs 1, 2, 5 in spirit): few long streams.
-The reference's corpora cannot travel to the GPU box, so the streams are text-like synthetic data of the
-same sizes: one 768,771 B stream (calgary/book1's size), the 29 Calgary+Canterbury file sizes, and
-12 blocks of <= 1 MiB.  Reports MB/s of raw input for the three mappings (lane, warp, split encoder) and for the CPU oracle."""
+"""Latency-bound configurations (BASELINE.json configs 1, 2, 5): few long streams, on the reference's own corpora
+(tests/golden/corpora/corpora.tar.xz, byte-identical to /root/reference/resources): calgary/book1 as one stream,
+the 29 Calgary + Canterbury files one stream each, and resources/large (bible.txt, world192.txt, seeded E.coli
+stand-in) in 1 MiB blocks with the frequency_bits / code_bits sweep.  Reports MB/s of raw input for the three
+mappings (lane, warp, split encoder) and for the CPU oracle; asserts every mapping's bytes equal the oracle's."""
 import json, os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,14 +10,16 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import redux_b200 as rb
 import oracle_lib as o
 
-CORPUS = [111261, 768771, 610856, 102400, 377109, 21504, 246814, 53161, 82199, 46526, 13286, 11954, 38105,
-          513216, 39611, 71646, 49379, 93695, 148481, 125179, 24603, 11150, 3721, 1029744, 419235, 471162,
-          513216, 38240, 4227]
-CONFIGS = {"config1_one_stream_768771B": [768771], "config2_29_corpus_sized_streams": CORPUS,
-           "config5_12_blocks_1MiB": [1048576] * 9 + [901664, 311129, 444386]}
+import corpora_fixture as cf
 
-def text_like(n, seed):
-    return rb.generate_blocks_host(1 + 4 * seed, 1, n, 0x5EED202610180000)       # class 1 = text-like
+FILES = cf.corpora()
+MIB = 1 << 20
+CONFIGS = {
+    "config1_book1_one_stream": [FILES["calgary/book1"]],
+    "config2_calgary_canterbury_29_streams": [FILES[n] for n in sorted(FILES) if n.startswith(("calgary/", "canterbury/"))],
+    "config5_large_in_1MiB_blocks": cf.blocks_of(FILES["large/bible.txt"], MIB) + cf.blocks_of(FILES["large/world192.txt"], MIB)
+                                    + cf.blocks_of(cf.ecoli_stand_in(), MIB),
+}
 
 def run(ctx, sched, data, off, model, reps=3):
     ctx.set_schedule(sched)
@@ -35,15 +38,18 @@ SWEEP = [(8, 10, 16), (8, 14, 16), (8, 16, 18), (8, 20, 22), (8, 22, 24), (8, 24
 
 
 def main():
-    ctx = rb.Context([0])
+    one = rb.Context([0])
+    ng = torch.cuda.device_count()
+    every = rb.Context(list(range(ng))) if ng > 1 else one      # config 5: the block list sharded over all GPUs of the box
     res = {}
-    for name, sizes in CONFIGS.items():
-        blocks = [text_like(n, i) for i, n in enumerate(sizes)]
-        data = np.concatenate(blocks)
+    for name, blocks_b in CONFIGS.items():
+        ctx = every if name.startswith("config5") else one
+        sizes = [len(b) for b in blocks_b]
+        data = np.frombuffer(b"".join(blocks_b), dtype=np.uint8)
         off = np.zeros(len(sizes) + 1, dtype=np.uint64); np.cumsum(sizes, out=off[1:])
         for params in (SWEEP if name.startswith("config5") else ((8, 14, 16), (8, 22, 24), (8, 30, 32))):
             model = rb.AdaptiveTreeModel(rb.Parameters(*params))
-            row = {}
+            row = {"devices": ng if name.startswith("config5") else 1, "streams": len(sizes), "raw_bytes": int(data.size)}
             ref = None
             for sched, label in ((rb.SCHED_LANE, "lane"), (rb.SCHED_WARP, "warp"), (rb.SCHED_SPLIT, "split")):
                 te, td, comp, coff = run(ctx, sched, data, off, model)
