@@ -534,6 +534,17 @@ struct BitWindowReg {
     }
 };
 
+// 1 / x to 1 ulp (MUFU.RCP); x is a range in [2, 2^32], far from the denormal and overflow cases __fdividef guards
+__device__ __forceinline__ float rcp_approx(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
 // Largest total frequency for which the float estimate of value = X / range is within one of the quotient.
 constexpr uint32_t kQuotientMaxCount = 1u << 20;
 
@@ -569,7 +580,7 @@ struct LaneDecoderAl {
         const uint32_t rm1 = (H - L) >> sh;
         const P X = C::mulr(count, (V - L) >> sh) - 1;
         P plo = 0, phi = C::mulr(count - eof_freq, rm1);      // node 256 = cum(256) = count - freq(EOF)
-        TW *p = tab.t;                                        // row of node i: the descent's position
+        uint32_t I = 0;                                       // i * 32: the descent's position, in table entries
         const bool is_eof = X >= phi;
         if (CLS == kNarrow) {
             // two tree levels per round (adaptive_tree.rs:119-127 unrolled by two): the candidates i+m,
@@ -580,16 +591,16 @@ struct LaneDecoderAl {
                 const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;      // nodes i+1, i+3 are odd
                 // (caching the twelve possible nodes of the second round as well was measured slower: 28.7 vs 27.4 ms)
                 const bool cached = m == 128;
-                const uint32_t ar = cached ? top_a : (uint32_t)p[m << 5];
-                const uint32_t br = cached ? top_b : (uint32_t)p[(h << 5) + oddadj];
-                const uint32_t cr = cached ? top_c : (uint32_t)p[((m + h) << 5) + oddadj];
+                const uint32_t ar = cached ? top_a : (uint32_t)tab.t[I + (uint32_t)(m << 5)];
+                const uint32_t br = cached ? top_b : (uint32_t)tab.t[(int)I + (h << 5) + oddadj];
+                const uint32_t cr = cached ? top_c : (uint32_t)tab.t[(int)I + ((m + h) << 5) + oddadj];
                 const P pa = C::mul_add((FULL ? 0u : (uint32_t)m) + ar, rm1, plo);
                 const P pb = C::mul_add((FULL ? 0u : (uint32_t)h) + br, rm1, plo);
                 const P pc = C::mul_add((FULL ? 0u : (uint32_t)h) + cr, rm1, pa);
                 const bool ra = X >= pa;                                        // first-level decision
                 const P p2 = ra ? pc : pb;                                      // second-level boundary
                 const bool r2 = X >= p2;                                        // second-level decision
-                TW *pm = p + (ra ? (m << 5) : 0);                               // row of the node the second level starts from
+                const uint32_t Im = I + (ra ? (uint32_t)(m << 5) : 0u);         // the node the second level starts from
                 if (UPD) {
                     // a left turn = the node covers the symbol from above = it is on the symbol's update path
                     const uint32_t v2 = (ra ? cr : br) + 1u;
@@ -597,44 +608,44 @@ struct LaneDecoderAl {
                         if (!ra) top_a += 1u;
                         if (!r2) { if (ra) top_c = v2; else top_b = v2; }
                     } else {
-                        if (!ra) p[m << 5] = (TW)(ar + 1u);
-                        if (!r2) pm[(h << 5) + oddadj] = (TW)v2;
+                        if (!ra) tab.t[I + (uint32_t)(m << 5)] = (TW)(ar + 1u);
+                        if (!r2) tab.t[(int)Im + (h << 5) + oddadj] = (TW)v2;
                     }
                 }
                 phi = r2 ? (ra ? phi : pa) : p2;
                 plo = r2 ? p2 : (ra ? pa : plo);
-                p = pm + (r2 ? (h << 5) : 0);
+                I = Im + (r2 ? (uint32_t)(h << 5) : 0u);
             }
         } else if (count > kQuotientMaxCount) {
             // 64-bit products, very long streams: the plain product-domain descent
 #pragma unroll
             for (int m = 128; m >= 2; m >>= 1) {              // even nodes i + m
                 // nodes 128, 64 and 192 are the register copies (the shared-memory ones are stale while ADAPT runs)
-                const bool low_half = p == tab.t;             // m == 64: node 64 or node 192
-                const uint32_t tr = m == 128 ? top_a : m == 64 ? (low_half ? top_b : top_c) : (uint32_t)p[m << 5];
+                const bool low_half = I == 0;                 // m == 64: node 64 or node 192
+                const uint32_t tr = m == 128 ? top_a : m == 64 ? (low_half ? top_b : top_c) : (uint32_t)tab.t[I + (uint32_t)(m << 5)];
                 const P pr = C::mul_add((FULL ? 0u : (uint32_t)m) + tr, rm1, plo);
                 const bool right = X >= pr;
                 if (UPD && !right) {
                     if (m == 128) top_a += 1u;
                     else if (m == 64) { if (low_half) top_b += 1u; else top_c += 1u; }
-                    else p[m << 5] = (TW)(tr + 1u);
+                    else tab.t[I + (uint32_t)(m << 5)] = (TW)(tr + 1u);
                 }
-                if (right) { p += m << 5; plo = pr; } else { phi = pr; }
+                if (right) { I += (uint32_t)(m << 5); plo = pr; } else { phi = pr; }
             }
             {                                                 // m = 1: odd node i + 1
-                const uint32_t tr = p[32 + LaneTable<TW>::kOddAdj];
+                const uint32_t tr = tab.t[(int)I + 32 + LaneTable<TW>::kOddAdj];
                 const P pr = C::mul_add((FULL ? 0u : 1u) + tr, rm1, plo);
                 const bool right = X >= pr;
-                if (UPD && !right) p[32 + LaneTable<TW>::kOddAdj] = (TW)(tr + 1u);
-                if (right) { p += 32; plo = pr; } else { phi = pr; }
+                if (UPD && !right) tab.t[(int)I + 32 + LaneTable<TW>::kOddAdj] = (TW)(tr + 1u);
+                if (right) { I += 32u; plo = pr; } else { phi = pr; }
             }
         } else {
             // 64-bit products: get the reference's value = X / range (src/codec.rs:131) FIRST -- a float
             // estimate made exact by one remainder check -- and search in the 32-bit value domain, two
             // tree levels per round like the narrow class.  The estimate is within one of the quotient
-            // because the quotient is < count <= 2^20: relative error 2^-24 (X) + 2^-24 (range) + 2^-22
-            // (division) keeps the absolute error below 0.4.
-            uint32_t v = (uint32_t)__fdividef(__ull2float_rn((unsigned long long)X), (float)rm1 + 1.0f);
+            // because the quotient is < count <= 2^20: relative error 2^-24 (X) + 2^-24 (range) + 2^-23
+            // (MUFU.RCP) + 2^-24 (product) keeps the absolute error below 0.4.
+            uint32_t v = (uint32_t)(__ull2float_rn((unsigned long long)X) * rcp_approx((float)rm1 + 1.0f));
             const P pv = C::mulr(v, rm1);                     // v * range
             if (pv > X) v -= 1u;                              // estimate one too high
             else if (X - pv > (P)rm1) v += 1u;                // one too low (remainder >= range)
@@ -644,34 +655,34 @@ struct LaneDecoderAl {
                 const int h = m >> 1;
                 const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;
                 const bool cached = m == 128;
-                const uint32_t ar = cached ? top_a : (uint32_t)p[m << 5];
-                const uint32_t br = cached ? top_b : (uint32_t)p[(h << 5) + oddadj];
-                const uint32_t cr = cached ? top_c : (uint32_t)p[((m + h) << 5) + oddadj];
+                const uint32_t ar = cached ? top_a : (uint32_t)tab.t[I + (uint32_t)(m << 5)];
+                const uint32_t br = cached ? top_b : (uint32_t)tab.t[(int)I + (h << 5) + oddadj];
+                const uint32_t cr = cached ? top_c : (uint32_t)tab.t[(int)I + ((m + h) << 5) + oddadj];
                 const uint32_t a = lo + (FULL ? 0u : (uint32_t)m) + ar;
                 const uint32_t b = lo + (FULL ? 0u : (uint32_t)h) + br;
                 const uint32_t cc = a + (FULL ? 0u : (uint32_t)h) + cr;
                 const bool ra = v >= a;
                 const uint32_t p2 = ra ? cc : b;
                 const bool r2 = v >= p2;
-                TW *pm = p + (ra ? (m << 5) : 0);
+                const uint32_t Im = I + (ra ? (uint32_t)(m << 5) : 0u);
                 if (UPD) {
                     const uint32_t v2 = (ra ? cr : br) + 1u;
                     if (cached) {
                         if (!ra) top_a += 1u;
                         if (!r2) { if (ra) top_c = v2; else top_b = v2; }
                     } else {
-                        if (!ra) p[m << 5] = (TW)(ar + 1u);
-                        if (!r2) pm[(h << 5) + oddadj] = (TW)v2;
+                        if (!ra) tab.t[I + (uint32_t)(m << 5)] = (TW)(ar + 1u);
+                        if (!r2) tab.t[(int)Im + (h << 5) + oddadj] = (TW)v2;
                     }
                 }
                 hi = r2 ? (ra ? hi : a) : p2;
                 lo = r2 ? p2 : (ra ? a : lo);
-                p = pm + (r2 ? (h << 5) : 0);
+                I = Im + (r2 ? (uint32_t)(h << 5) : 0u);
             }
             plo = C::mulr(lo, rm1);
             phi = C::mulr(hi, rm1);
         }
-        const uint32_t sym = (uint32_t)(p - tab.t) >> 5;
+        const uint32_t sym = I >> 5;
         // src/codec.rs:133-134 (for the EOF symbol the descent's products are meaningless but harmless: the step
         // leaves through the single exit below before anything is stored or consumed)
         const uint32_t nh2 = ~((uint32_t)C::divc(phi, g, count) * one + (L - 1u));

@@ -19,3 +19,6 @@ if [ "$2" = "ncu" ]; then
   ncu --set full --clock-control none --import-source on -k regex:lane -s 6 -c 2 -f -o gpurun_out/${tag}_wide_prof $cmd > gpurun_out/${tag}_wide_ncu.log 2>&1
   ls -la gpurun_out/${tag}_wide_prof.ncu-rep
 fi
+python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-classes --blocks 16384 --params 8,30,34 > gpurun_out/${tag}_bench_huge.json 2>&1; echo "huge rc=$?"; python -c "
+import json; d=json.loads([l for l in open('gpurun_out/${tag}_bench_huge.json') if l.startswith('{')][-1]); print('8,30,34 x16384', d['roofline']['kernel_ms'], d['value'])"
+python scripts/bench_underfilled.py > gpurun_out/${tag}_underfilled.log 2>&1; echo "underfilled rc=$?"; cat gpurun_out/${tag}_underfilled.log
