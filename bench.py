@@ -69,8 +69,27 @@ def arith_dtype(params):
     return "u32" if params[1] + params[2] <= 30 else "u64"
 
 
+_corpus = None
+
+
+def text_corpus():
+    """The corpus the text class (block index & 3 == 1) cuts its windows from: the concatenation, in sorted path
+    order, of the Calgary and Canterbury corpora -- 6,040,451 bytes from the
+    fixture tests/golden/corpora/corpora.tar.xz (byte-identical to the reference's resources/)."""
+    global _corpus
+    if _corpus is None:
+        import numpy as np
+
+        import corpora_fixture as cf
+        files = cf.corpora()
+        names = sorted(n for n in files if n.startswith(("calgary/", "canterbury/")))
+        _corpus = np.frombuffer(b"".join(files[n] for n in names), dtype=np.uint8)
+        assert _corpus.size == 6040451
+    return _corpus
+
+
 def workload_name(a, world=1):
-    per = "%d x %d B mixed-entropy blocks, Adaptive%sModel, Parameters(%s)" % (
+    per = "%d x %d B mixed-entropy blocks (uniform / Calgary+Canterbury window / geometric / sparse), Adaptive%sModel, Parameters(%s)" % (
         a.blocks, a.block_len, a.model.capitalize(), a.params)
     return per if world == 1 else "%d ranks x (%s) = %d blocks" % (world, per, world * a.blocks)
 
@@ -128,7 +147,7 @@ def cpu_round_trip(a, n_sample, threads, first_block=0, keep_streams=False):
     kind = o.TREE if a.model == "tree" else o.LINEAR
     params = tuple(int(x) for x in a.params.split(","))
     L = a.block_len
-    raw = o.generate_blocks(first_block, n_sample, L, SEED)
+    raw = o.generate_blocks(first_block, n_sample, L, SEED, corpus=text_corpus())
     off = np.arange(n_sample + 1, dtype=np.uint64) * np.uint64(L)
     t0 = time.perf_counter()
     rc, slots, slot_off, out_len, status = o.compress_batch(raw, off, kind, params, threads)
@@ -415,6 +434,7 @@ def run_ours(a):
     params = tuple(int(x) for x in a.params.split(","))
     n, L = a.blocks, a.block_len
     ctx = rb.Context([local])
+    ctx.set_text_corpus(text_corpus())
     first_block = sharding.weak_first_block(n, rank)      # weak scaling: distinct blocks per rank
 
     # ---- synthetic batch, resident in HBM

@@ -218,6 +218,13 @@ int redux_generate_blocks_device(redux_ctx_t *ctx, int device, void *stream, uin
                                  uint64_t seed);
 void redux_generate_blocks_host(uint8_t *out, uint64_t first_block, uint64_t n_blocks,
                                 uint64_t block_len, uint64_t seed);
+/* Text class from a corpus: with a corpus of at least block_len bytes, blocks of
+ * class 1 are block_len-byte windows of it at a per-block pseudo-random offset instead of the table-driven stand-in.
+ * redux_ctx_set_text_corpus uploads it to every device of the context for redux_generate_blocks_device (NULL, 0
+ * clears it); redux_generate_blocks_host_ex is the CPU twin. */
+int redux_ctx_set_text_corpus(redux_ctx_t *ctx, const uint8_t *corpus, uint64_t corpus_len);
+void redux_generate_blocks_host_ex(uint8_t *out, uint64_t first_block, uint64_t n_blocks,
+                                   uint64_t block_len, uint64_t seed, const uint8_t *corpus, uint64_t corpus_len);
 
 /* ---- debug / self-test hooks (host arithmetic only; used by the CPU tests)
  * Exact-division magic for divisor d and numerators < 2^nbits (DESIGN.md "count reciprocal"):

@@ -120,6 +120,8 @@ int oracle_decompress_batch(int kind, uint64_t s, uint64_t f, uint64_t c,
 /* synth_blocks.c: the synthetic mixed-entropy blocks of BASELINE.json configs 3-4 (block index & 3: uniform /
  * text-like / geometric / sparse), n_blocks blocks of block_len bytes starting at block index first_block. */
 void oracle_generate_blocks(uint8_t *out, uint64_t first_block, uint64_t n_blocks, uint64_t block_len, uint64_t seed);
+void oracle_generate_blocks_ex(uint8_t *out, uint64_t first_block, uint64_t n_blocks, uint64_t block_len, uint64_t seed,
+                               const uint8_t *corpus, uint64_t corpus_len);
 
 #ifdef __cplusplus
 }

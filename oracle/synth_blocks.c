@@ -11,6 +11,8 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include "redux_oracle.h"
+
 static uint64_t mix64(uint64_t z)
 {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -32,12 +34,26 @@ static void text_table(uint8_t lut[256])
 
 void oracle_generate_blocks(uint8_t *out, uint64_t first_block, uint64_t n_blocks, uint64_t block_len, uint64_t seed)
 {
+    oracle_generate_blocks_ex(out, first_block, n_blocks, block_len, seed, NULL, 0);
+}
+
+/* With a corpus of at least block_len bytes the text class (block & 3 == 1) is a block_len-byte window of it at
+ * offset draw(block, 2^64 - 2) % (corpus_len - block_len + 1). */
+void oracle_generate_blocks_ex(uint8_t *out, uint64_t first_block, uint64_t n_blocks, uint64_t block_len, uint64_t seed,
+                               const uint8_t *corpus, uint64_t corpus_len)
+{
     uint8_t lut[256];
     text_table(lut);
     for (uint64_t b = 0; b < n_blocks; ++b) {
         const uint64_t block = first_block + b;
         const uint32_t cls = (uint32_t)(block & 3);
         uint8_t *dst = out + b * block_len;
+        if (cls == 1 && corpus && block_len && corpus_len >= block_len) {
+            const uint64_t at = mix64(seed + block * 0xD1342543DE82EF95ull + (~(uint64_t)0) * 0x9E3779B97F4A7C15ull)
+                                % (corpus_len - block_len + 1);
+            for (uint64_t i = 0; i < block_len; ++i) dst[i] = corpus[at + i];
+            continue;
+        }
         for (uint64_t w = 0; w * 8 < block_len; ++w) {
             const uint64_t r = mix64(seed + block * 0xD1342543DE82EF95ull + (w + 1) * 0x9E3779B97F4A7C15ull);
             const uint64_t r2 = mix64(r ^ 0xA5A5A5A5A5A5A5A5ull);

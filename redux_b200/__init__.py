@@ -128,6 +128,9 @@ def lib():
     L.redux_generate_blocks_device.argtypes = [vp, i32, vp, vp, u64, u64, u64, u64]
     L.redux_generate_blocks_host.argtypes = [vp, u64, u64, u64, u64]
     L.redux_generate_blocks_host.restype = None
+    L.redux_generate_blocks_host_ex.argtypes = [vp, u64, u64, u64, u64, vp, u64]
+    L.redux_generate_blocks_host_ex.restype = None
+    L.redux_ctx_set_text_corpus.argtypes = [vp, vp, u64]
     L.redux_debug_magic.argtypes = [u64, u32, i32, C.POINTER(u64), C.POINTER(u32)]
     L.redux_debug_magic_divide.argtypes = [u64, u64, u32, i32]
     L.redux_debug_magic_divide.restype = u64
@@ -465,14 +468,26 @@ class Context:
                                                   _ptr(d_raw), _ptr(d_raw_offsets), _ptr(d_raw_lens), _ptr(d_consumed),
                                                   _ptr(d_status)), self)
 
+    def set_text_corpus(self, corpus):
+        """bytes / uint8 array (or None): the corpus the synthetic generator cuts its text-class blocks from."""
+        if corpus is None:
+            _raise(lib().redux_ctx_set_text_corpus(self._h, None, 0), self)
+            return
+        a = np.frombuffer(bytes(corpus), dtype=np.uint8) if not isinstance(corpus, np.ndarray) else np.ascontiguousarray(corpus, dtype=np.uint8)
+        _raise(lib().redux_ctx_set_text_corpus(self._h, a.ctypes.data, a.size), self)
+
     def generate_blocks_device(self, d_out, first_block, n_blocks, block_len, seed, device=0, stream=None):
         _raise(lib().redux_generate_blocks_device(self._h, device, stream, _ptr(d_out), first_block, n_blocks,
                                                   block_len, seed), self)
 
 
-def generate_blocks_host(first_block, n_blocks, block_len, seed):
+def generate_blocks_host(first_block, n_blocks, block_len, seed, corpus=None):
     out = np.empty(n_blocks * block_len, dtype=np.uint8)
-    lib().redux_generate_blocks_host(out.ctypes.data, first_block, n_blocks, block_len, seed)
+    if corpus is None:
+        lib().redux_generate_blocks_host(out.ctypes.data, first_block, n_blocks, block_len, seed)
+    else:
+        a = np.frombuffer(bytes(corpus), dtype=np.uint8) if not isinstance(corpus, np.ndarray) else np.ascontiguousarray(corpus, dtype=np.uint8)
+        lib().redux_generate_blocks_host_ex(out.ctypes.data, first_block, n_blocks, block_len, seed, a.ctypes.data, a.size)
     return out
 
 

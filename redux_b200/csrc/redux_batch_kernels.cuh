@@ -123,14 +123,15 @@ compact_kernel(const uint8_t *__restrict__ slots, uint64_t stride, const uint32_
 // Synthetic blocks: thread <-> one 8-byte group (gen_group of redux_common.cuh).
 // ---------------------------------------------------------------------------------------------
 __global__ void generate_kernel(uint8_t *out, uint64_t first_block, uint64_t n_blocks,
-                                uint64_t block_len, uint64_t seed, const uint8_t *text_lut)
+                                uint64_t block_len, uint64_t seed, const uint8_t *text_lut,
+                                const uint8_t *corpus, uint64_t corpus_len)
 {
     const uint64_t groups_per_block = (block_len + 7) >> 3;
     const uint64_t total = n_blocks * groups_per_block;
     for (uint64_t gidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < total;
          gidx += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t b = gidx / groups_per_block, w = gidx - b * groups_per_block;
-        const uint64_t v = gen_group(seed, first_block + b, w, text_lut);
+        const uint64_t v = gen_group(seed, first_block + b, w, text_lut, corpus, corpus_len, block_len);
         uint8_t *p = out + b * block_len + w * 8;
         const uint64_t left = block_len - w * 8;
         if (left >= 8 && (((uintptr_t)p & 7) == 0)) *reinterpret_cast<uint64_t *>(p) = v;

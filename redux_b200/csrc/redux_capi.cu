@@ -88,6 +88,7 @@ struct DeviceState {
     DevBuf split_hist, split_pairs;            // split encoder: chunk histograms, per-position ranges
     DevBuf gen_tabs, gen_init, gen_freq;       // generic path: Fenwick columns, start tree, uploaded frequencies
     uint8_t *text_lut = nullptr;
+    DevBuf corpus; uint64_t corpus_len = 0;    // text-class corpus of the synthetic generator (redux_ctx_set_text_corpus)
     std::vector<MagicEntry> magics;
     bool smem_set = false;
     // The device-resident entry points share ONE workspace per device (slots, sizes, generic-path columns ...).
@@ -555,12 +556,18 @@ extern "C" int redux_debug_lane_occupancy(int *enc_ctas_per_sm, int *dec_ctas_pe
 extern "C" void redux_generate_blocks_host(uint8_t *out, uint64_t first_block, uint64_t n_blocks,
                                            uint64_t block_len, uint64_t seed)
 {
+    redux_generate_blocks_host_ex(out, first_block, n_blocks, block_len, seed, nullptr, 0);
+}
+
+extern "C" void redux_generate_blocks_host_ex(uint8_t *out, uint64_t first_block, uint64_t n_blocks,
+                                              uint64_t block_len, uint64_t seed, const uint8_t *corpus, uint64_t corpus_len)
+{
     uint8_t lut[256];
     for (uint32_t u = 0; u < 256; ++u) lut[u] = text_symbol(u);
     const uint64_t groups = (block_len + 7) >> 3;
     for (uint64_t b = 0; b < n_blocks; ++b)
         for (uint64_t w = 0; w < groups; ++w) {
-            uint64_t v = gen_group(seed, first_block + b, w, lut);
+            uint64_t v = gen_group(seed, first_block + b, w, lut, corpus, corpus_len, block_len);
             for (uint64_t j = 0; j < 8 && w * 8 + j < block_len; ++j)
                 out[b * block_len + w * 8 + j] = (uint8_t)(v >> (8 * j));
         }
@@ -657,7 +664,7 @@ extern "C" void redux_ctx_destroy(redux_ctx_t *ctx)
         for (int i = 0; i < kPipeStreams; ++i) if (d.pipe[i]) cudaStreamDestroy(d.pipe[i]);
         for (HostBuf *b : {&d.pin_off, &d.pin_status, &d.pin_aux0, &d.pin_aux1}) b->release();
         for (DevBuf *b : {&d.slots, &d.sizes, &d.flag, &d.st_in, &d.st_off, &d.st_out, &d.st_ooff,
-                          &d.st_status, &d.st_aux0, &d.st_aux1, &d.st_roff, &d.gen_tabs, &d.gen_init, &d.gen_freq, &d.split_hist, &d.split_pairs}) b->release();
+                          &d.st_status, &d.st_aux0, &d.st_aux1, &d.st_roff, &d.corpus, &d.gen_tabs, &d.gen_init, &d.gen_freq, &d.split_hist, &d.split_pairs}) b->release();
         for (auto &m : d.magics) cudaFree(m.ptr);
         if (d.text_lut) cudaFree(d.text_lut);
     }
@@ -690,6 +697,20 @@ extern "C" int redux_ctx_timing_collect(redux_ctx_t *ctx, double *ms, uint64_t *
     }
     ctx->spans.clear();
     return rc;
+}
+
+extern "C" int redux_ctx_set_text_corpus(redux_ctx_t *ctx, const uint8_t *corpus, uint64_t corpus_len)
+{
+    if (!ctx || (!corpus && corpus_len)) return REDUX_INVALID_INPUT;
+    for (auto &d : ctx->devs) {
+        DeviceGuard g(d.device);
+        d.corpus_len = 0;
+        if (!corpus_len) continue;
+        CU_TRY(ctx, d.corpus.reserve(corpus_len));
+        CU_TRY(ctx, cudaMemcpy(d.corpus.p, corpus, corpus_len, cudaMemcpyHostToDevice));
+        d.corpus_len = corpus_len;
+    }
+    return REDUX_OK;
 }
 
 extern "C" int redux_ctx_set_schedule(redux_ctx_t *ctx, int sched)
@@ -878,7 +899,8 @@ extern "C" int redux_generate_blocks_device(redux_ctx_t *ctx, int device, void *
     cudaStream_t s = (cudaStream_t)stream_;   // NULL = the default stream, as in CUDA
     {
         KernelTimer kt(ctx, device, s, REDUX_KERNEL_GENERATE);
-        generate_kernel<<<148 * 8, 256, 0, s>>>(d_out, first_block, n_blocks, block_len, seed, d->text_lut);
+        generate_kernel<<<148 * 8, 256, 0, s>>>(d_out, first_block, n_blocks, block_len, seed, d->text_lut,
+                                                (const uint8_t *)d->corpus.p, d->corpus_len);
     }
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());

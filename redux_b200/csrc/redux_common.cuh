@@ -206,7 +206,8 @@ RDX_HD LanePlan lane_plan(uint32_t f, uint32_t c, uint64_t max_block_len, uint32
 // GPU can fill any 8-byte group independently: draw(block, w) = mix(seed + block*K + (w+1)*GAMMA).
 // class = block & 3:
 //   0 uniform bytes                                   H ~ 8.0  bit/byte
-//   1 text-like: 256-entry Zipf table over 55 symbols H ~ 4.5
+//   1 text: a block-sized window of a corpus the caller supplies (bench.py: Calgary + Canterbury, H ~ 4.5-5),
+//     or, without one, a 256-entry Zipf table over 55 symbols  H ~ 4.5
 //   2 geometric: ctz of a 16-bit field                H ~ 2.0
 //   3 sparse: 0x00 with p = 63/64, else a random byte H ~ 0.24
 // (the reference's corpora cannot travel to the GPU box, so class 1 is a table-driven stand-in for
@@ -232,12 +233,24 @@ RDX_HD uint8_t text_symbol(uint32_t u8v) {
     }
     return (uint8_t)alphabet[63];
 }
-// 8 output bytes for 64-bit group w of `block`
-RDX_HD uint64_t gen_group(uint64_t seed, uint64_t block, uint64_t w, const uint8_t *text_lut) {
+// Text class with a corpus ("64 KiB window of the concatenation of calgary +
+// canterbury at offset next() % (L - 65536)"): the block is corpus[off, off + block_len), off drawn once per block.
+RDX_HD uint64_t text_window_offset(uint64_t seed, uint64_t block, uint64_t corpus_len, uint64_t block_len) {
+    return gen_draw(seed, block, ~(uint64_t)0 - 1) % (corpus_len - block_len + 1);
+}
+// 8 output bytes for 64-bit group w of `block`.  corpus == NULL (or shorter than a block): the table-driven
+// stand-in for the text class.
+RDX_HD uint64_t gen_group(uint64_t seed, uint64_t block, uint64_t w, const uint8_t *text_lut,
+                          const uint8_t *corpus = nullptr, uint64_t corpus_len = 0, uint64_t block_len = 0) {
     uint64_t r = gen_draw(seed, block, w);
     uint32_t cls = (uint32_t)(block & 3);
     if (cls == 0) return r;
     uint64_t out = 0;
+    if (cls == 1 && corpus && corpus_len >= block_len && block_len) {
+        const uint64_t at = text_window_offset(seed, block, corpus_len, block_len) + 8 * w;
+        for (int j = 0; j < 8; ++j) out |= (uint64_t)(at + j < corpus_len ? corpus[at + j] : 0) << (8 * j);
+        return out;
+    }
     if (cls == 1) {
         for (int j = 0; j < 8; ++j) out |= (uint64_t)text_lut[(r >> (8 * j)) & 255] << (8 * j);
         return out;

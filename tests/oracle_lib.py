@@ -62,6 +62,8 @@ def lib():
     L = C.CDLL(_SO)
     L.oracle_generate_blocks.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]
     L.oracle_generate_blocks.restype = None
+    L.oracle_generate_blocks_ex.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.oracle_generate_blocks_ex.restype = None
     u64, p8, pu64 = C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)
     L.oracle_params_new.argtypes = [u64, u64, u64, C.POINTER(Params)]
     L.oracle_params_new.restype = C.c_int
@@ -175,10 +177,15 @@ def trained_frequencies(train, kind=TREE, params=(8, 30, 32)):
     return (tab[:, 1] - tab[:, 0]).astype(np.uint32)
 
 
-def generate_blocks(first_block, n_blocks, block_len, seed):
-    """The synthetic mixed-entropy blocks of the benchmark, from the oracle side (oracle/synth_blocks.c)."""
+def generate_blocks(first_block, n_blocks, block_len, seed, corpus=None):
+    """The synthetic mixed-entropy blocks of the benchmark, from the oracle side (oracle/synth_blocks.c); corpus =
+    the bytes the text class cuts its windows from (None: the table-driven stand-in)."""
     out = np.empty(n_blocks * block_len, dtype=np.uint8)
-    lib().oracle_generate_blocks(out.ctypes.data, first_block, n_blocks, block_len, seed)
+    if corpus is None:
+        lib().oracle_generate_blocks(out.ctypes.data, first_block, n_blocks, block_len, seed)
+    else:
+        a = np.frombuffer(bytes(corpus), dtype=np.uint8) if not isinstance(corpus, np.ndarray) else np.ascontiguousarray(corpus, dtype=np.uint8)
+        lib().oracle_generate_blocks_ex(out.ctypes.data, first_block, n_blocks, block_len, seed, a.ctypes.data, a.size)
     return out
 
 

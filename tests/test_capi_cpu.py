@@ -231,3 +231,16 @@ def test_oracle_side_generator_equals_the_products_host_generator():
     seed = 0x5EED202610180000
     for first, n, L in ((0, 64, 4096), (5, 9, 1001), (65530, 8, 65536), (3, 4, 7)):
         assert (o.generate_blocks(first, n, L, seed) == rb.generate_blocks_host(first, n, L, seed)).all()
+    # with a corpus: the text class is a window of it, the other classes are unchanged
+    corpus = np.frombuffer(bytes(range(256)) * 300, dtype=np.uint8)            # 76,800 bytes
+    for first, n, L in ((0, 16, 4096), (1, 5, 65536), (1, 3, 76800)):
+        a, b = o.generate_blocks(first, n, L, seed, corpus=corpus), rb.generate_blocks_host(first, n, L, seed, corpus=corpus)
+        assert (a == b).all()
+        plain = rb.generate_blocks_host(first, n, L, seed)
+        for i in range(n):
+            blk = a[i * L:(i + 1) * L]
+            if (first + i) & 3 == 1:
+                at = int(blk[0])
+                assert (blk == corpus[at:at + L]).all()                       # a window: consecutive byte values
+            else:
+                assert (blk == plain[i * L:(i + 1) * L]).all()
