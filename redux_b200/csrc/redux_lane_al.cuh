@@ -27,6 +27,12 @@
 
 namespace rdx {
 
+// Pins a launch constant in a register.  ptxas re-reads kernel parameters from the constant bank at every use (one
+// LDCU per use and per symbol step in the encoder's loops); adding a zero it cannot know to be zero -- the top bit
+// of a block offset loaded from memory -- makes the value a computed one that lives in a register.
+__device__ __forceinline__ uint32_t pinned(uint32_t x, uint64_t loaded_offset) { return x + (uint32_t)(loaded_offset >> 63); }
+__device__ __forceinline__ uint64_t pinned(uint64_t x, uint64_t loaded_offset) { return x + (loaded_offset >> 63); }
+
 // count-leading-zeros of a NON-ZERO word as one instruction (FLO.U32.SH)
 __device__ __forceinline__ uint32_t clz_nz(uint32_t x) {
 #if defined(__CUDA_ARCH__)
@@ -374,7 +380,8 @@ encode_lane_al_kernel(const LaneEncJob job)
 
     const uint64_t off = job.in_off[blk];
     const uint32_t len = (uint32_t)(job.in_off[blk + 1] - off);
-    const uint32_t c = job.c, sh = 32 - c, one = job.one;
+    const uint32_t c = job.c, sh = 32 - c;
+    const uint32_t one = pinned(job.one, off);
     const uint32_t count0 = job.count0, eof_freq = job.eof_freq;   // 257 and 1 for a fresh model
     const M *magic = reinterpret_cast<const M *>(job.magic);
     const uint32_t tcap = job.tcap;
@@ -419,7 +426,8 @@ encode_lane_al_kernel(const LaneEncJob job)
     }
     while (t < n_adapt) adapt_step(src.next());
     // frozen phase (adaptive_tree.rs:84): total == FMAX, table and reciprocal are constant
-    const M gfz = C::mk(job.gf_m, job.gf_sh);              // reciprocal of FMAX, from the constant bank
+    // reciprocal of FMAX: launch constants (no global load in the frozen loop)
+    const M gfz = C::mk(pinned(job.gf_m, off), pinned(job.gf_sh, off));
     const uint32_t countf = count0 + n_adapt;
     const uint32_t cum256f = countf - eof_freq;
     if (t < len) {
@@ -579,10 +587,12 @@ struct LaneDecoderAl {
         // X = (value-low+1)*count - 1
         const uint32_t rm1 = (H - L) >> sh;
         const P X = C::mulr(count, (V - L) >> sh) - 1;
-        P plo = 0, phi = C::mulr(count - eof_freq, rm1);      // node 256 = cum(256) = count - freq(EOF)
+        P plo = 0, phi = 0;
         uint32_t I = 0;                                       // i * 32: the descent's position, in table entries
-        const bool is_eof = X >= phi;
+        bool is_eof;                                          // value >= cum(256) = count - freq(EOF): the EOF symbol
         if (CLS == kNarrow) {
+            phi = C::mulr(count - eof_freq, rm1);             // node 256
+            is_eof = X >= phi;
             // two tree levels per round (adaptive_tree.rs:119-127 unrolled by two): the candidates i+m,
             // i+m/2 and i+m+m/2 are loaded together -- 4 dependent shared-memory round trips, not 8
 #pragma unroll
@@ -618,6 +628,8 @@ struct LaneDecoderAl {
             }
         } else if (count > kQuotientMaxCount) {
             // 64-bit products, very long streams: the plain product-domain descent
+            phi = C::mulr(count - eof_freq, rm1);
+            is_eof = X >= phi;
 #pragma unroll
             for (int m = 128; m >= 2; m >>= 1) {              // even nodes i + m
                 // nodes 128, 64 and 192 are the register copies (the shared-memory ones are stale while ADAPT runs)
@@ -650,6 +662,7 @@ struct LaneDecoderAl {
             if (pv > X) v -= 1u;                              // estimate one too high
             else if (X - pv > (P)rm1) v += 1u;                // one too low (remainder >= range)
             uint32_t lo = 0, hi = count - eof_freq;           // cum(i) <= v < hi tracked in the value domain
+            is_eof = v >= hi;                                 // the quotient is in hand: no product for node 256
 #pragma unroll
             for (int m = 128; m >= 2; m >>= 2) {
                 const int h = m >> 1;

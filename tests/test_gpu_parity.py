@@ -269,6 +269,20 @@ def test_generator_device_equals_host(ctx):
                                stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert (d.cpu().numpy() == rb.generate_blocks_host(7, n, L, SEED)).all()
+    # text class cut from a corpus (what bench.py does with Calgary + Canterbury): device == host == oracle side
+    import corpora_fixture as cf
+    files = cf.corpora()
+    corpus = np.frombuffer(b"".join(files[k] for k in sorted(files) if k.startswith("canterbury/")), dtype=np.uint8)
+    ctx.set_text_corpus(corpus)
+    try:
+        ctx.generate_blocks_device(d, 7, n, L, SEED, device=torch.cuda.current_device(),
+                                   stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        host = rb.generate_blocks_host(7, n, L, SEED, corpus=corpus)
+        assert (d.cpu().numpy() == host).all() and (host == o.generate_blocks(7, n, L, SEED, corpus=corpus)).all()
+        assert corpus.tobytes().find(host[2 * L:3 * L].tobytes()) >= 0          # block index 9: class 1 = a window
+    finally:
+        ctx.set_text_corpus(None)
 
 
 def test_device_resident_batch_roundtrip_and_sampled_parity(ctx):
