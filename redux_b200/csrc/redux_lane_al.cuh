@@ -556,6 +556,66 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // Largest total frequency for which the float estimate of value = X / range is within one of the quotient.
 constexpr uint32_t kQuotientMaxCount = 1u << 20;
 
+// ------------------------------------------------------------------ byte sink (decoder output), phase-free
+// Decoded symbols leave as aligned 32-bit words whatever the byte phase of the stream's slot: the bytes not yet
+// stored sit in the TOP c8 bits of `top` (oldest lowest), four new symbols wv complete the word
+// (wv << c8) | (top >> (32 - c8)) -- one funnel shift -- and leave their own top c8 bits pending.  Every lane runs
+// the same instructions whether its slot starts at byte phase 0, 1, 2 or 3.  That matters: round 1 walked to a
+// word boundary symbol by symbol first, the lanes of a warp left that head loop after 0..3 steps, and because the
+// decoder's loops are left by early returns the compiler's convergence barriers never brought them back together:
+// a warp whose 32 slots had four different phases ran the whole stream four times over (measured 4.0x,
+// scripts/bench_alignment.py; any ragged batch, e.g. the corpus files one stream each, is such a warp).
+// The slot's first word also holds up to three bytes of the neighbouring slot, which must not be written: that one
+// word is stored to a private scratch location instead and its own bytes follow byte-wise at the end.
+struct ByteSinkF {
+    uint32_t *w0;        // the slot's first (aligned) word
+    uint32_t *pw;        // aligned word holding the next pending byte
+    uint32_t *wp;        // where the next word store goes: pw, or the scratch word while the first word is open
+    uint32_t top, c8;    // pending bytes: the top c8 bits of `top`
+    uint32_t ph;         // byte phase of the slot inside its first word
+
+    __device__ __forceinline__ void init(uint8_t *d, uint32_t *scratch) {
+        const uintptr_t a = (uintptr_t)d;
+        w0 = pw = reinterpret_cast<uint32_t *>(a & ~(uintptr_t)3);
+        ph = (uint32_t)(a & 3);
+        c8 = 8 * ph;                      // the neighbour's bytes in the first word count as pending (never stored)
+        top = 0;
+        wp = ph ? scratch : pw;
+    }
+    __device__ __forceinline__ void store_word(uint32_t word) {
+        *wp = word;
+        ++pw;
+        wp = pw;
+    }
+    // four symbols (byte j = symbol j)
+    __device__ __forceinline__ void put4(uint32_t wv) {
+        store_word(__funnelshift_l(top, wv, c8));
+        top = wv;
+    }
+    // one symbol (the steps after the last whole group of four of a phase)
+    __device__ __forceinline__ void put(uint32_t sym) {
+        top = (top >> 8) | (sym << 24);
+        c8 += 8;
+        if (c8 == 32) { store_word(top); c8 = 0; }
+    }
+    __device__ __forceinline__ void partial(uint32_t wv, uint32_t nbytes) {       // the first nbytes symbols of wv
+        for (uint32_t j = 0; j < nbytes; ++j) put((wv >> (8 * j)) & 0xFFu);
+    }
+    // the bytes no word store carried: the pending ones, and our part of the slot's first word
+    __device__ __forceinline__ void finish(const uint32_t *scratch) const {
+        const bool head_open = pw == w0;                                           // no word was ever completed
+        uint8_t *b = reinterpret_cast<uint8_t *>(pw);
+        const uint32_t c = c8 >> 3;
+        for (uint32_t i = head_open ? ph : 0u; i < c; ++i)
+            b[i] = (uint8_t)(top >> (32 - c8 + 8 * i));
+        if (!head_open && ph) {
+            const uint32_t headw = *scratch;                                       // this thread's own earlier store
+            uint8_t *h = reinterpret_cast<uint8_t *>(w0);
+            for (uint32_t j = ph; j < 4; ++j) h[j] = (uint8_t)(headw >> (8 * j));
+        }
+    }
+};
+
 // ------------------------------------------------------------------ decoder
 // STG: a step never consumes more than 16 bits (code_bits <= 16), see BitWindow::advance.
 template <typename TW, int CLS, bool FULL, bool C32, bool STG>
@@ -565,7 +625,7 @@ struct LaneDecoderAl {
     using M = typename C::M;
     LaneTable2<TW, FULL> tab;
     BitWindow bw;
-    ByteSink out;
+    ByteSinkF out;
     uint32_t L, H, V;    // left-aligned low / high (src/codec.rs:11-24) and the code-value window
     uint32_t sh, one, t, left;   // one == 1 << sh, opaque to the compiler (keeps q * one + L an IMAD)
     uint32_t count0, eof_freq;   // start total / frequency of EOF (257 / 1 for a fresh model)
@@ -730,8 +790,8 @@ struct LaneDecoderAl {
     // position, loaded four positions ahead in the main loop); otherwise the table is frozen at `count_frozen`.
     // PEEK: the output slot is full -- decode one more symbol only to tell a complete stream (EOF next) from
     // Err(Eof) and from OUT_CAPACITY.
-    // Once the output position is word aligned the loop runs four symbols per round: their bytes go to
-    // constant positions of one store and the per-symbol sink and loop bookkeeping disappears.
+    // The loop runs four symbols per round from the first symbol on (ByteSinkF takes them at any byte phase): their
+    // bytes go to constant positions of one word and the per-symbol sink and loop bookkeeping disappears.
     template <bool ADAPT, bool PEEK>
     __device__ __forceinline__ void run(uint32_t t_end, const M *magic, uint32_t count_frozen, const M &g_frozen) {
         // the three nodes of the first descent round (128, 64, 192) live in registers: one shared-memory round
@@ -743,12 +803,6 @@ struct LaneDecoderAl {
             return;
         }
         M gn = ADAPT ? C::ldm(magic + t) : g_frozen;          // reciprocal of position t, loaded one ahead
-        while (t < t_end && !out.word_aligned()) {
-            const M g = gn;
-            if (ADAPT) gn = C::ldm(magic + t + 1);
-            if (!step<ADAPT, false>(sym, g, count_frozen)) return;
-            out.put(sym);
-        }
         if (t + 4 <= t_end) {
             M g0 = gn, g1 = gn, g2 = gn, g3 = gn;
             if (ADAPT) { g1 = C::ldm(magic + t + 1); g2 = C::ldm(magic + t + 2); g3 = C::ldm(magic + t + 3); }
@@ -765,7 +819,7 @@ struct LaneDecoderAl {
                 if (!step<ADAPT, false>(sym, g2, count_frozen)) { out.partial(wv, 2); return; }
                 wv |= sym << 16;
                 if (!step<ADAPT, false>(sym, g3, count_frozen)) { out.partial(wv, 3); return; }
-                out.put_word(wv | (sym << 24));
+                out.put4(wv | (sym << 24));
                 if (ADAPT) { g0 = m0; g1 = m1; g2 = m2; g3 = m3; }
             }
             gn = g0;
@@ -807,7 +861,8 @@ decode_lane_al_kernel(const LaneDecJob job)
     const uint32_t cap = cap64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)cap64;
     const uint32_t total_bits = (uint32_t)clen * 8;
     d.sh = 32 - c; d.one = job.one; d.count0 = job.count0; d.eof_freq = job.eof_freq;
-    d.out.init(job.raw + roff);
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(job.consumed + blk);   // this thread's own word until the end
+    d.out.init(job.raw + roff, scratch);
     d.st = 0; d.t = 0;
     d.L = 0; d.H = 0xFFFFFFFFu; d.V = 0; d.left = 0;
     const M *magic = reinterpret_cast<const M *>(job.magic);
@@ -831,7 +886,7 @@ decode_lane_al_kernel(const LaneDecJob job)
         d.template run<false, false>(cap, magic, d.count0 + tcap, gf);
         if (d.st == 0) d.template run<false, true>(d.t + 1, magic, d.count0 + tcap, gf);
     }
-    d.out.finish();
+    d.out.finish(scratch);
     job.raw_len[blk] = d.t;
     job.consumed[blk] = (total_bits - d.left + 7) >> 3;
     job.status[blk] = d.st < 0 ? 0 : d.st;
