@@ -802,28 +802,27 @@ struct LaneDecoderAl {
             if (t < t_end) (void)step<ADAPT, true>(sym, ADAPT ? C::ldm(magic + t) : g_frozen, count_frozen);
             return;
         }
-        M gn = ADAPT ? C::ldm(magic + t) : g_frozen;          // reciprocal of position t, loaded one ahead
-        if (t + 4 <= t_end) {
-            M g0 = gn, g1 = gn, g2 = gn, g3 = gn;
-            if (ADAPT) { g1 = C::ldm(magic + t + 1); g2 = C::ldm(magic + t + 2); g3 = C::ldm(magic + t + 3); }
-            while (t + 4 <= t_end) {
-                M m0 = g0, m1 = g1, m2 = g2, m3 = g3;
-                if (ADAPT) {
-                    m0 = C::ldm(magic + t + 4); m1 = C::ldm(magic + t + 5); m2 = C::ldm(magic + t + 6); m3 = C::ldm(magic + t + 7);
-                }
-                uint32_t wv;
-                if (!step<ADAPT, false>(sym, g0, count_frozen)) return;
-                wv = sym;
-                if (!step<ADAPT, false>(sym, g1, count_frozen)) { out.partial(wv, 1); return; }
-                wv |= sym << 8;
-                if (!step<ADAPT, false>(sym, g2, count_frozen)) { out.partial(wv, 2); return; }
-                wv |= sym << 16;
-                if (!step<ADAPT, false>(sym, g3, count_frozen)) { out.partial(wv, 3); return; }
-                out.put4(wv | (sym << 24));
-                if (ADAPT) { g0 = m0; g1 = m1; g2 = m2; g3 = m3; }
+        // reciprocals of positions t .. t+3, each loaded four positions ahead (the table is padded: reading past the
+        // last position a short stream uses is harmless)
+        M g0 = ADAPT ? C::ldm(magic + t) : g_frozen, g1 = g0, g2 = g0, g3 = g0;
+        if (ADAPT) { g1 = C::ldm(magic + t + 1); g2 = C::ldm(magic + t + 2); g3 = C::ldm(magic + t + 3); }
+        while (t + 4 <= t_end) {
+            M m0 = g0, m1 = g1, m2 = g2, m3 = g3;
+            if (ADAPT) {
+                m0 = C::ldm(magic + t + 4); m1 = C::ldm(magic + t + 5); m2 = C::ldm(magic + t + 6); m3 = C::ldm(magic + t + 7);
             }
-            gn = g0;
+            uint32_t wv;
+            if (!step<ADAPT, false>(sym, g0, count_frozen)) return;
+            wv = sym;
+            if (!step<ADAPT, false>(sym, g1, count_frozen)) { out.partial(wv, 1); return; }
+            wv |= sym << 8;
+            if (!step<ADAPT, false>(sym, g2, count_frozen)) { out.partial(wv, 2); return; }
+            wv |= sym << 16;
+            if (!step<ADAPT, false>(sym, g3, count_frozen)) { out.partial(wv, 3); return; }
+            out.put4(wv | (sym << 24));
+            if (ADAPT) { g0 = m0; g1 = m1; g2 = m2; g3 = m3; }
         }
+        M gn = g0;
         while (t < t_end) {
             const M g = gn;
             if (ADAPT) gn = C::ldm(magic + t + 1);

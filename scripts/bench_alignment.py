@@ -69,6 +69,17 @@ def main():
             assert ok and int(st.abs().max()) == 0 and bool((rl == L).all())
             res["%s %s" % (params, name)] = {"encode_ms": round(te, 3), "decode_ms": round(td, 3)}
             print(params, name, res["%s %s" % (params, name)], flush=True)
+        # encoder: raw blocks at byte phases 0..3 of the input buffer (lengths L - (i % 4), back to back)
+        lens = np.array([L - (i % 4) for i in range(n)], dtype=np.int64)
+        ioff = np.zeros(n + 1, dtype=np.int64); np.cumsum(lens, out=ioff[1:])
+        cin = torch.from_numpy(np.concatenate([blocks[i][:lens[i]] for i in range(n)])).cuda()
+        d_ioff = torch.from_numpy(ioff).cuda()
+        cap = n * L * 2
+        comp = torch.empty(cap, dtype=torch.uint8, device="cuda"); coff = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+        st = torch.zeros(n, dtype=torch.int32, device="cuda")
+        te = timed(lambda: ctx.encode_batch_device(cin, d_ioff, n, L, comp, cap, coff, st, model, device=0, stream=stream))
+        res["%s encoder input at byte phases 0..3" % (params,)] = {"encode_ms": round(te, 3)}
+        print(params, "encoder input at byte phases 0..3", round(te, 3), flush=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_alignment.json"), "w"), indent=1)
 
 

@@ -412,6 +412,46 @@ def test_generic_many_blocks_share_columns(ctx):
     assert (status == 0).all() and (back[: n * L] == raw).all()      # 96 bytes = 64 whole 12-bit symbols
 
 
+def test_decode_time_does_not_depend_on_slot_alignment():
+    """Lanes of one warp decode into slots at different byte phases (any ragged batch).  Round 1 walked each lane to a
+    word boundary first and the warp never reconverged afterwards: it ran the whole stream once per phase (4.0x,
+    scripts/bench_alignment.py).  The phase-free sink keeps the warp together: same bytes, and the mixed-phase launch
+    takes as long as the aligned one (generous bound: 1.5x; both launches are timed back to back on one stream)."""
+    import torch
+    n, L = 32, 65536
+    params = (8, 14, 16)
+    model = rb.AdaptiveTreeModel(rb.Parameters(*params))
+    blocks = [rb.generate_blocks_host(1 + 4 * i, 1, L, SEED) for i in range(n)]
+    with rb.Context([0]) as c:
+        c.set_schedule(rb.SCHED_LANE)
+        data, off = concat([b.tobytes() for b in blocks])
+        comp, coff, st = c.encode_batch(data, off, model)
+        stream = torch.cuda.current_stream().cuda_stream
+        d_comp = torch.from_numpy(np.concatenate([comp, np.zeros(64, np.uint8)])).cuda()
+        d_coff = torch.from_numpy(coff.astype(np.int64)).cuda()
+        times = {}
+        for name, pads in (("aligned", [16] * n), ("mixed", [((i % 4) + 1) % 4 for i in range(n)])):
+            roff = np.zeros(n + 1, dtype=np.int64)
+            for i in range(n):
+                roff[i + 1] = roff[i] + L + pads[i]
+            d_roff = torch.from_numpy(roff).cuda()
+            back = torch.zeros(int(roff[-1]) + 64, dtype=torch.uint8, device="cuda")
+            rl = torch.zeros(n, dtype=torch.int64, device="cuda"); cons = torch.zeros(n, dtype=torch.int64, device="cuda")
+            dst = torch.zeros(n, dtype=torch.int32, device="cuda")
+            run = lambda: c.decode_batch_device(d_comp, d_coff, n, L + 16, back, d_roff, rl, cons, dst, model, device=0, stream=stream)
+            run(); torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record(); run(); run(); ev[1].record(); ev[1].synchronize()
+            times[name] = ev[0].elapsed_time(ev[1]) / 2
+            assert int(dst.abs().max()) == 0 and bool((rl == L).all())
+            host = back.cpu().numpy()
+            for i in (0, 1, 2, 3, 17, 31):
+                assert (host[int(roff[i]):int(roff[i]) + L] == blocks[i]).all(), (name, i)
+                if pads[i]:
+                    assert (host[int(roff[i]) + L:int(roff[i + 1])] == 0).all(), "bytes between the slots were written"
+        assert times["mixed"] < 1.5 * times["aligned"], times
+
+
 def test_two_ctas_per_sm_fit_the_shared_memory_budget():
     """The tuned kernels' shared memory (7 x 16 KiB tables + one 4-byte staging slot per thread) is sized to the
     byte for two CTAs per SM = 448 resident streams per SM, which is what puts 65,536 blocks in ONE wave on 148
