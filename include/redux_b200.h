@@ -35,7 +35,7 @@ extern "C" {
 #define REDUX_MODEL_TREE   1    /* AdaptiveTreeModel::new   (src/model/adaptive_tree.rs:36-48)   */
 
 /* ---- stream-to-thread mapping (new; the reference is single-threaded) */
-#define REDUX_SCHED_AUTO 0      /* choose by batch shape */
+#define REDUX_SCHED_AUTO 0      /* choose by batch shape: encode = SPLIT below 512 streams, else LANE; decode = LANE */
 #define REDUX_SCHED_LANE 1      /* one stream per lane, 32 streams per warp: throughput mapping */
 #define REDUX_SCHED_WARP 2      /* one stream per warp, lanes cooperate per symbol: latency mapping */
 #define REDUX_SCHED_SPLIT 3     /* encode: model phase parallel over the positions of a stream, then one coder warp

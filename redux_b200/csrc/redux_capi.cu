@@ -186,17 +186,25 @@ struct Plan {
     uint64_t max_len = 0;   // longest block of the launch
 };
 
-// REDUX_SCHED_AUTO: with this few streams both mappings are bound by the serial latency of the longest
-// stream; measured on B200 (scripts/bench_small.py, profiles/r01_small_batches.json) the cooperating
-// warp decodes 1.3-1.45x faster and encodes within -10%..+15% of a lone lane.  Above it, 32 streams per
-// warp win on issue slots.
+// REDUX_SCHED_AUTO, encode: below this many streams the split encoder (parallel model phase + one coder warp per
+// stream) beats 32 streams per warp (profiles/r02_small_batches_corpora.json, profiles/r02_underfilled.json: 512
+// blocks of 64 KiB encode in 7.6 ms split vs 9.6 ms lane; 2,048 blocks 19.7 vs 9.8 ms).  The plain warp encoder never
+// wins (29 corpus files: 31 MB/s against 62 lane and 86 split), so AUTO falls back to the lane mapping, not to it.
 constexpr uint64_t kWarpAutoMaxBlocks = 512;
 
-bool choose_warp(const redux_ctx *ctx, uint64_t n_blocks)
+bool choose_warp(const redux_ctx *ctx, uint64_t)
 {
-    if (ctx->sched == REDUX_SCHED_WARP || ctx->sched == REDUX_SCHED_SPLIT) return true;
-    if (ctx->sched == REDUX_SCHED_LANE) return false;
-    return n_blocks < kWarpAutoMaxBlocks;
+    return ctx->sched == REDUX_SCHED_WARP || ctx->sched == REDUX_SCHED_SPLIT;
+}
+
+// Decode: REDUX_SCHED_AUTO always takes the lane mapping.  Since the decoder's output sink is phase-free (round 2) a
+// lane decodes every class faster than a cooperating warp at every batch size measured, ragged corpus batches
+// included (profiles/r02_small_batches_corpora.json: 29 files 28.6 vs 20.0 MB/s, 12 x 1 MiB 51.3 vs 35.9 MB/s at
+// (8,14,16); 15.2 vs 13.6 and 27.3 vs 24.3 MB/s at (8,30,32); one stream 4.9 vs 3.4 / 2.6 vs 2.3 MB/s).  The warp
+// decoder stays selectable (REDUX_SCHED_WARP / REDUX_SCHED_SPLIT).
+bool choose_warp_decode(const redux_ctx *ctx, uint64_t)
+{
+    return ctx->sched == REDUX_SCHED_WARP || ctx->sched == REDUX_SCHED_SPLIT;
 }
 
 // The split encoder needs 8 bytes of workspace per input position; beyond 2 GB the warp mapping is used.
@@ -869,7 +877,7 @@ extern "C" int redux_decode_batch_device(redux_ctx_t *ctx, int device, void *str
     if ((rc = check_kind(ctx, model_kind))) return rc;
     Plan pl;
     if ((rc = make_plan(ctx, params, max_block_len, &pl))) return rc;
-    pl.warp = !pl.generic && !pl.pretrained && choose_warp(ctx, n_blocks) && !(ctx->sched == REDUX_SCHED_AUTO && pl.cls == kNarrow);
+    pl.warp = !pl.generic && !pl.pretrained && choose_warp_decode(ctx, n_blocks);
     DeviceState *d = find_dev(ctx, device);
     if (!d) return fail(ctx, REDUX_INVALID_INPUT, "device is not part of this context");
     if (n_blocks == 0) return REDUX_OK;
@@ -1272,8 +1280,7 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     Plan pl;
     int rc = make_plan(ctx, p, max_len, &pl);
     if (rc) return rc;
-    // small batches: the cooperating warp decodes 64-bit-product classes faster, a lone lane the narrow class
-    pl.warp = !pl.generic && !pl.pretrained && choose_warp(ctx, sh.count) && !(ctx->sched == REDUX_SCHED_AUTO && pl.cls == kNarrow);
+    pl.warp = !pl.generic && !pl.pretrained && choose_warp_decode(ctx, sh.count);
     const std::vector<Shard> chunks = pl.generic ? std::vector<Shard>{{0, sh.count}} : make_chunks(sh.count, -1);
     const size_t nc = chunks.size();
     CU_TRY(ctx, d->st_in.reserve(cbytes + 32));

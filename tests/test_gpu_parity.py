@@ -103,8 +103,8 @@ def test_kat_vectors_single_stream(ctx):
 
 
 def test_auto_schedule_gives_the_same_bytes():
-    """REDUX_SCHED_AUTO picks the warp mapping for small batches and the lane mapping for large ones;
-    the bytes never depend on the mapping."""
+    """REDUX_SCHED_AUTO picks the split encoder for small batches and the lane mapping otherwise (decode: always the
+    lane mapping); the bytes never depend on the mapping."""
     n, L = 2600, 1500
     raw = rb.generate_blocks_host(0, n, L, SEED)
     off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
