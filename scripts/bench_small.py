@@ -42,7 +42,10 @@ def main():
     ng = torch.cuda.device_count()
     every = rb.Context(list(range(ng))) if ng > 1 else one      # config 5: the block list sharded over all GPUs of the box
     res = {}
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     for name, blocks_b in CONFIGS.items():
+        if only and not name.startswith(only):
+            continue
         ctx = every if name.startswith("config5") else one
         sizes = [len(b) for b in blocks_b]
         data = np.frombuffer(b"".join(blocks_b), dtype=np.uint8)
@@ -70,7 +73,7 @@ def main():
                                  "threads": threads}
             res["%s %s" % (name, params)] = row
             print(name, params, json.dumps(row), flush=True)
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_small.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bench_small%s.json" % (("_" + only + "_%dgpu" % ng) if only else "")), "w"), indent=1)
 
 if __name__ == "__main__":
     main()

@@ -17,3 +17,4 @@ try:
 except Exception as e:
     print("bench failed", e); print(open("gpurun_out/${tag}_bench_n$N.err").read()[-3000:])
 PY
+python scripts/bench_small.py config5 > gpurun_out/${tag}_config5.log 2>&1; echo "config5 rc=$?"; tail -7 gpurun_out/${tag}_config5.log | cut -c1-330
