@@ -1,5 +1,5 @@
 """bench.py's JSON line against the driver's contract, checked on the committed record of the last GPU run
-(profiles/r01_final5_bench_default.json, profiles/r01_final5_bench_reference_arm.json).  No GPU needed."""
+(profiles/r02_bench_default.json, profiles/r02_bench_reference_arm.json).  No GPU needed."""
 import json
 import os
 
@@ -12,7 +12,7 @@ def _load(name):
 
 
 def test_our_arm_line_has_every_contract_key():
-    d = _load("r01_final5_bench_default.json")
+    d = _load("r02_bench_default.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
@@ -34,18 +34,24 @@ def test_our_arm_line_has_every_contract_key():
         assert k in e, k
     assert e["h2d_bytes_per_step"] > d["config"]["per_gpu_raw_bytes"] and e["value"] < d["value"]
     assert e["value"] > 50 * c["value"]                                      # the GPU path end to end vs the host cores
+    # round 2: the line proves what it claims and carries the other classes, the copy ceiling and the host-memory kinds
+    assert d["parity_checked_blocks"] >= 64
+    assert set(d["classes"]) == {"8,22,24", "8,30,32"} and all(v["decode_ms"] > 0 for v in d["classes"].values())
+    assert 0.5 < e["frac_of_copy_ceiling"] <= 1.0 and e["copy_ceiling"]["value"] >= e["value"]
+    assert e["pageable"]["value"] < e["value"] and e["registered"]["value"] > 0.8 * e["value"]
+    assert "Calgary+Canterbury" in d["config"]["workload"]
     k = d["clocks"]
     assert not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert k["sm_mhz"] and k["sm_mhz"] > 0.9 * k["sm_max_mhz"]
 
 
 def test_reference_arm_line():
-    d = _load("r01_final5_bench_reference_arm.json")
+    d = _load("r02_bench_reference_arm.json")
     assert d["impl"] == "reference" and d["unit"] == "MB/s" and d["gpu_launches"] == 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
-    ours = _load("r01_final5_bench_default.json")
+    ours = _load("r02_bench_default.json")
     assert d["metric"] == ours["metric"] and d["config"]["workload"] == ours["config"]["workload"]
 
 
