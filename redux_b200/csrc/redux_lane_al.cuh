@@ -464,15 +464,18 @@ encode_lane_al_kernel(const LaneEncJob job)
 }
 
 // ------------------------------------------------------------------ bit window (decoder input)
-// w0:w1 are two consecutive big-endian stream words; win() = the 32 stream bits starting at bit `pos`
-// of w0.  The word after w1 is in the staging slot (StageSlot) or on its way there: a refill reads the slot
-// and requests the following word.  EVERY step closes one cp.async group, refill or not, so "my word was
-// requested at least two steps ago" translates to "all but the youngest group have landed":
-// advance<KEEP = 1> never waits for a copy younger than two symbol steps.  That holds when a lane cannot
-// refill in two consecutive steps, i.e. a step consumes at most 16 bits (code_bits <= 16); wider classes use
-// KEEP = 0 (one step of distance -- their steps are twice as long).
+// w0:w1:w2 are three consecutive big-endian stream words; the window = the 32 stream bits starting at bit `pos` of
+// w0.  The word after w2 is in the staging slot (StageSlot) or on its way there: a refill shifts the words, reads the
+// slot and requests the following word.
+// A step that consumes at most 16 bits (code_bits <= 16, the decoder's STG flag) lets the refill run every SECOND
+// step: after a refill pos < 32, two steps add at most 32, so one word always suffices, the first step of a pair
+// reads its window from w0:w1 (pos < 32) and the second from w0:w1 or w1:w2 (pos < 48).  That halves the refill
+// code issued per symbol (13 instructions, all predicated: some lane of the warp refills almost every step) and the
+// cp.async bookkeeping (commit + wait + the three padding LDS ptxas puts before every LDGSTS), and every wait finds a
+// copy that was requested a whole pair of steps (> 1,000 cycles) earlier -- nothing younger exists.  Wider classes
+// refill after every step (their steps are twice as long).
 struct BitWindow {
-    uint32_t w0, w1, pos;
+    uint32_t w0, w1, w2, pos;
     const uint32_t *base;
     uint32_t idx, last;     // next word to request / last word that may be read
     StageSlot slot;
@@ -493,19 +496,24 @@ struct BitWindow {
         slot.init(slot_mem);
         w0 = swap(word_at(0)); w1 = swap(word_at(1));
         const uint32_t first = win();
-        w0 = w1; w1 = swap(word_at(2));
-        idx = 3;
+        w0 = w1; w1 = swap(word_at(2)); w2 = swap(word_at(3));
+        idx = 4;
         request();
         StageSlot::commit();
-        StageSlot::commit();        // an empty group: the first step may already leave one group in flight
         return first;
     }
+    // pos < 32 (after every refill point)
     __device__ __forceinline__ uint32_t win() const { return __funnelshift_l(w1, w0, pos); }
-    template <int KEEP>
-    __device__ __forceinline__ void advance(uint32_t n) {                   // n <= 32 (KEEP = 0) / 16 (KEEP = 1)
-        StageSlot::wait<KEEP>();
+    // pos < 64 (second step of a pair); the funnel shift takes its count modulo 32
+    __device__ __forceinline__ uint32_t win2() const {
+        const bool up = pos >= 32;
+        return __funnelshift_l(up ? w2 : w1, up ? w1 : w0, pos);
+    }
+    __device__ __forceinline__ void skip(uint32_t n) { pos += n; }          // first step of a pair: n <= 16, no refill
+    __device__ __forceinline__ void advance(uint32_t n) {                   // refill point; pos + n < 64
+        StageSlot::wait<0>();
         pos += n;
-        if (pos >= 32) { pos -= 32; w0 = w1; w1 = swap(slot.read()); request(); }
+        if (pos >= 32) { pos -= 32; w0 = w1; w1 = w2; w2 = swap(slot.read()); request(); }
         StageSlot::commit();
     }
 };
@@ -617,7 +625,7 @@ struct ByteSinkF {
 };
 
 // ------------------------------------------------------------------ decoder
-// STG: a step never consumes more than 16 bits (code_bits <= 16), see BitWindow::advance.
+// STG: a step never consumes more than 16 bits (code_bits <= 16): pairs of steps share one refill point (BitWindow).
 template <typename TW, int CLS, bool FULL, bool C32, bool STG>
 struct LaneDecoderAl {
     using C = Cls<CLS>;
@@ -639,7 +647,9 @@ struct LaneDecoderAl {
     // the nodes at which the descent to s turned LEFT (each covers s from above; the last one is the unstored
     // node 256), and the descent has just loaded their values -- so each left turn stores value + 1.  After a
     // step that returns false the stream is finished, so what such a step stored no longer matters.
-    template <bool ADAPT, bool PEEK>
+    // MODE: 0 = refill after the step (window at pos < 32); 1 / 2 = first / second step of a pair that refills once
+    // (STG only, see BitWindow).
+    template <bool ADAPT, bool PEEK, int MODE = 0>
     __device__ __forceinline__ bool step(uint32_t &sym_out, const M &g, uint32_t count_frozen) {
         constexpr bool UPD = ADAPT && !PEEK;
         const uint32_t count = ADAPT ? count0 + t : count_frozen;
@@ -774,11 +784,11 @@ struct LaneDecoderAl {
         }
         left -= n;
         // E1/E2: shift the window, pulling the next stream bits in; E3: keep the MSB, drop k bits below it
-        const uint32_t win = bw.win();
+        const uint32_t win = MODE == 2 ? bw.win2() : bw.win();
         const uint32_t A = __funnelshift_lc(win, V, n1);
         const uint32_t Bv = __funnelshift_lc(shl_c(win, n1), A, k);
         V = (A & 0x80000000u) | (Bv & 0x7FFFFFFFu);
-        bw.template advance<STG ? 1 : 0>(n);
+        if (MODE == 1) bw.skip(n); else bw.advance(n);
         L = shl_c(l2, n) & 0x7FFFFFFFu;
         H = ~shl_c(nh2, n) | 0x80000000u;
         sym_out = sym;
@@ -811,14 +821,15 @@ struct LaneDecoderAl {
             if (ADAPT) {
                 m0 = C::ldm(magic + t + 4); m1 = C::ldm(magic + t + 5); m2 = C::ldm(magic + t + 6); m3 = C::ldm(magic + t + 7);
             }
+            constexpr int M1 = STG ? 1 : 0, M2 = STG ? 2 : 0;     // pairs of steps share one refill point
             uint32_t wv;
-            if (!step<ADAPT, false>(sym, g0, count_frozen)) return;
+            if (!step<ADAPT, false, M1>(sym, g0, count_frozen)) return;
             wv = sym;
-            if (!step<ADAPT, false>(sym, g1, count_frozen)) { out.partial(wv, 1); return; }
+            if (!step<ADAPT, false, M2>(sym, g1, count_frozen)) { out.partial(wv, 1); return; }
             wv |= sym << 8;
-            if (!step<ADAPT, false>(sym, g2, count_frozen)) { out.partial(wv, 2); return; }
+            if (!step<ADAPT, false, M1>(sym, g2, count_frozen)) { out.partial(wv, 2); return; }
             wv |= sym << 16;
-            if (!step<ADAPT, false>(sym, g3, count_frozen)) { out.partial(wv, 3); return; }
+            if (!step<ADAPT, false, M2>(sym, g3, count_frozen)) { out.partial(wv, 3); return; }
             out.put4(wv | (sym << 24));
             if (ADAPT) { g0 = m0; g1 = m1; g2 = m2; g3 = m3; }
         }
@@ -874,17 +885,15 @@ decode_lane_al_kernel(const LaneDecJob job)
         d.V = d.bw.init(job.comp + coff, (uint32_t)clen, lane_stage_slot<TW>(smem_u4));
         d.left = total_bits - c;
     }
+    // The two phases are entered unconditionally (a stream that already failed gets an empty range of positions): a
+    // divergent `if` around them would be one more convergence scope every symbol step's exit has to break out of.
     const M g0 = D::C::ldm(magic);
-    if (d.st == 0) {
-        const uint32_t e1 = tcap < cap ? tcap : cap;
-        d.template run<true, false>(e1, magic, 0, g0);
-        if (d.st == 0 && d.t == cap && cap < tcap) d.template run<true, true>(d.t + 1, magic, 0, g0);
-    }
-    if (d.st == 0) {
-        const M gf = D::C::mk(job.gf_m, job.gf_sh);           // reciprocal of FMAX, from the constant bank
-        d.template run<false, false>(cap, magic, d.count0 + tcap, gf);
-        if (d.st == 0) d.template run<false, true>(d.t + 1, magic, d.count0 + tcap, gf);
-    }
+    const uint32_t e1 = d.st != 0 ? 0u : (tcap < cap ? tcap : cap);
+    d.template run<true, false>(e1, magic, 0, g0);
+    if (d.st == 0 && d.t == cap && cap < tcap) d.template run<true, true>(d.t + 1, magic, 0, g0);
+    const M gf = D::C::mk(job.gf_m, job.gf_sh);               // reciprocal of FMAX: launch constants, no global load
+    d.template run<false, false>(d.st != 0 ? d.t : cap, magic, d.count0 + tcap, gf);
+    if (d.st == 0) d.template run<false, true>(d.t + 1, magic, d.count0 + tcap, gf);
     d.out.finish(scratch);
     job.raw_len[blk] = d.t;
     job.consumed[blk] = (total_bits - d.left + 7) >> 3;

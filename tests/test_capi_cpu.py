@@ -244,3 +244,42 @@ def test_oracle_side_generator_equals_the_products_host_generator():
                 assert (blk == corpus[at:at + L]).all()                       # a window: consecutive byte values
             else:
                 assert (blk == plain[i * L:(i + 1) * L]).all()
+
+
+def test_process_init_is_explicit_and_respects_the_applications_setting():
+    """Loading the library must not touch the process environment (round 1 set CUDA_DEVICE_MAX_CONNECTIONS from a
+    load-time constructor); redux_process_init() sets it to 32 only when the application has not set it."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import redux_b200 as rb\n"
+        "rb.lib()\n"
+        "before = os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS')\n"
+        "import ctypes\n"
+        "libc = ctypes.CDLL(None); libc.getenv.restype = ctypes.c_char_p\n"
+        "raw_before = libc.getenv(b'CUDA_DEVICE_MAX_CONNECTIONS')\n"
+        "v = rb.process_init()\n"
+        "raw_after = libc.getenv(b'CUDA_DEVICE_MAX_CONNECTIONS')\n"
+        "print(repr((raw_before, v, raw_after)))\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k != "CUDA_DEVICE_MAX_CONNECTIONS"}
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0, out.stderr[-1500:]
+    assert eval(out.stdout.strip().splitlines()[-1]) == (None, 32, b"32")          # untouched by loading, set by the call
+    env["CUDA_DEVICE_MAX_CONNECTIONS"] = "4"
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert eval(out.stdout.strip().splitlines()[-1]) == (b"4", 4, b"4")             # the application's setting wins
+
+
+def test_pinned_memory_entry_points_fail_loudly_without_a_device():
+    """No GPU here: page-locking needs CUDA, and the entry points say so instead of handing out pageable memory."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    p = C.c_void_p()
+    assert rb.lib().redux_host_alloc(4096, C.byref(p)) == rb.CUDA_ERROR and not p.value
+    buf = np.zeros(4096, dtype=np.uint8)
+    assert rb.lib().redux_host_register(buf.ctypes.data, buf.nbytes) == rb.CUDA_ERROR
+    assert rb.lib().redux_host_alloc(0, C.byref(p)) == rb.OK          # nothing to allocate

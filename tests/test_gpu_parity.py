@@ -452,6 +452,86 @@ def test_decode_time_does_not_depend_on_slot_alignment():
         assert times["mixed"] < 1.5 * times["aligned"], times
 
 
+def test_pinned_host_buffers_and_registered_buffers():
+    """redux_host_alloc / redux_host_register: the same bytes come out whatever kind of host memory the caller hands
+    in (pageable numpy, page-locked by the library, page-locked in place)."""
+    n, L = 300, 3000
+    raw = rb.generate_blocks_host(0, n, L, SEED)
+    off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+    model = rb.AdaptiveTreeModel(rb.Parameters(8, 14, 16))
+    with rb.Context([0]) as c:
+        ref, ref_off, _ = c.encode_batch(raw, off, model)
+        hb = rb.HostBuffer(raw.size)
+        hb.array[:] = raw
+        out = rb.HostBuffer(ref.size + 4096)
+        comp, coff, st = c.encode_batch(hb.array, off, model, out=out.array)
+        assert comp.tobytes() == ref.tobytes() and (coff == ref_off).all() and (st == 0).all()
+        reg = raw.copy()
+        rb.host_register(reg)
+        try:
+            comp2, coff2, _ = c.encode_batch(reg, off, model)
+            assert comp2.tobytes() == ref.tobytes()
+            back, rl, cons, st = c.decode_batch(comp2, coff2, off, model, raw=reg)      # decode into the registered buffer
+            assert (st == 0).all() and (reg == raw).all()
+        finally:
+            rb.host_unregister(reg)
+        comp = coff = None
+        hb.close(); out.close()
+
+
+def test_device_entry_points_take_a_trained_model():
+    """redux_encode_batch_device_ex / redux_decode_batch_device_ex: a model trained before the call, data resident in
+    HBM; bytes equal the oracle's compress() from the same trained model."""
+    import torch
+    n, L = 64, 5000
+    raw = rb.generate_blocks_host(0, n, L, SEED)
+    train = [int(x) for x in raw[:700]]
+    for params in ((8, 14, 16), (8, 30, 32)):
+        model = rb.AdaptiveTreeModel(rb.Parameters(*params)).train(train)
+        with rb.Context([0]) as c:
+            stream = torch.cuda.current_stream().cuda_stream
+            d_raw = torch.from_numpy(raw).cuda()
+            d_off = torch.arange(n + 1, dtype=torch.int64, device="cuda") * L
+            cap = 2 * n * L
+            d_comp = torch.empty(cap, dtype=torch.uint8, device="cuda"); d_coff = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+            d_st = torch.zeros(n, dtype=torch.int32, device="cuda")
+            c.encode_batch_device(d_raw, d_off, n, L, d_comp, cap, d_coff, d_st, model, device=0, stream=stream)
+            d_back = torch.empty(n * L, dtype=torch.uint8, device="cuda")
+            rl = torch.zeros(n, dtype=torch.int64, device="cuda"); cons = torch.zeros(n, dtype=torch.int64, device="cuda")
+            c.decode_batch_device(d_comp, d_coff, n, L, d_back, d_off, rl, cons, d_st, model, device=0, stream=stream)
+            torch.cuda.synchronize()
+            assert int(d_st.abs().max()) == 0 and torch.equal(d_back, d_raw)
+            comp, coff = d_comp.cpu().numpy(), d_coff.cpu().numpy()
+            for i in (0, 1, 31, 63):
+                want = o.compress_trained(raw[i * L:(i + 1) * L], train, o.TREE, params)[1]
+                assert comp[int(coff[i]):int(coff[i + 1])].tobytes() == want, (params, i)
+
+
+def test_device_calls_on_different_streams_do_not_share_the_workspace_unordered():
+    """One workspace per device: two encodes enqueued back to back on DIFFERENT streams must not overwrite each
+    other's slots; the library orders them on the device."""
+    import torch
+    n, L = 2048, 4096
+    model = rb.AdaptiveTreeModel(rb.Parameters(8, 14, 16))
+    with rb.Context([0]) as c:
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        bufs = []
+        for k, st in enumerate((s1, s2)):
+            d_raw = torch.from_numpy(rb.generate_blocks_host(k * n, n, L, SEED)).cuda()
+            bufs.append((st, d_raw, torch.empty(2 * n * L, dtype=torch.uint8, device="cuda"),
+                         torch.zeros(n + 1, dtype=torch.int64, device="cuda"), torch.zeros(n, dtype=torch.int32, device="cuda")))
+        d_off = torch.arange(n + 1, dtype=torch.int64, device="cuda") * L
+        torch.cuda.synchronize()
+        for st, d_raw, d_comp, d_coff, d_st in bufs:            # enqueued without any host synchronisation in between
+            c.encode_batch_device(d_raw, d_off, n, L, d_comp, 2 * n * L, d_coff, d_st, model, device=0, stream=st.cuda_stream)
+        torch.cuda.synchronize()
+        for k, (st, d_raw, d_comp, d_coff, d_st) in enumerate(bufs):
+            comp, coff = d_comp.cpu().numpy(), d_coff.cpu().numpy()
+            raw = d_raw.cpu().numpy()
+            for i in (0, 7, 1000, n - 1):
+                assert comp[int(coff[i]):int(coff[i + 1])].tobytes() == o.compress(raw[i * L:(i + 1) * L], o.TREE, (8, 14, 16))[1], (k, i)
+
+
 def test_two_ctas_per_sm_fit_the_shared_memory_budget():
     """The tuned kernels' shared memory (7 x 16 KiB tables + one 4-byte staging slot per thread) is sized to the
     byte for two CTAs per SM = 448 resident streams per SM, which is what puts 65,536 blocks in ONE wave on 148
