@@ -591,7 +591,11 @@ struct ByteSinkF {
         wp = ph ? scratch : pw;
     }
     __device__ __forceinline__ void store_word(uint32_t word) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("st.global.u32 [%0], %1;" :: "l"(wp), "r"(word) : "memory");    // both targets are global memory
+#else
         *wp = word;
+#endif
         ++pw;
         wp = pw;
     }
