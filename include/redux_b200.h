@@ -230,7 +230,8 @@ void redux_generate_blocks_host_ex(uint8_t *out, uint64_t first_block, uint64_t 
  * Exact-division magic for divisor d and numerators < 2^nbits (DESIGN.md "count reciprocal"):
  * floor(n/d) == mulhi(n, magic) >> shift. wide=0: 32-bit mulhi, wide=1: 64-bit mulhi, wide=2: the 65-bit magic of the
  * code_bits > 32 class (nbits ignored: exact for every 64-bit numerator; divide = (((n - t) >> 1) + t) >> (shift - 1),
- * t = mulhi64(n, magic)). */
+ * t = mulhi64(n, magic)); wide=3: the double reciprocal of the WIDE_D class (magic = the bits of 1.0/d, d < 2^17;
+ * exact for n = cum * range < 2^49 with cum <= d). */
 int redux_debug_magic(uint64_t d, uint32_t nbits, int wide, uint64_t *magic, uint32_t *shift);
 uint64_t redux_debug_magic_divide(uint64_t n, uint64_t magic, uint32_t shift, int wide);
 /* Closed-form renormalisation of one (low, high) pair: returns n1 (E1/E2 shifts) in

@@ -19,6 +19,10 @@ template <> struct MagicMaker<Magic64> {
     static __device__ Magic64 make(uint32_t d, uint32_t nbits) { return nbits ? make_magic64(d, nbits) : make_magic65(d); }
 };
 
+template <> struct MagicMaker<MagicD> {
+    static __device__ MagicD make(uint32_t d, uint32_t) { return make_magicd(d); }
+};
+
 // out[tt] = magic of count 257 + tt for numerators < 2^nbits
 template <typename M>
 __global__ void build_magic_kernel(M *out, uint32_t n, uint32_t nbits)

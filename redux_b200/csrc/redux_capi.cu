@@ -164,6 +164,11 @@ cudaError_t configure_kernels()
     RDX_CFG((encode_lane_al_kernel<uint32_t, kWide, true, C32>), s32)  RDX_CFG((decode_lane_al_kernel<uint32_t, kWide, true, C32, false>), s32)
     RDX_CFG_WIDE(false) RDX_CFG_WIDE(true)
 #undef RDX_CFG_WIDE
+    // WIDE_D (double-reciprocal division; 16-bit tables only, redux_common.cuh MagicD)
+#define RDX_CFG_WIDED(FULL, C32) \
+    RDX_CFG((encode_lane_al_kernel<uint16_t, kWideD, FULL, C32>), s16) RDX_CFG((decode_lane_al_kernel<uint16_t, kWideD, FULL, C32, false>), s16)
+    RDX_CFG_WIDED(true, false) RDX_CFG_WIDED(true, true) RDX_CFG_WIDED(false, false) RDX_CFG_WIDED(false, true)
+#undef RDX_CFG_WIDED
     // generic kernels: Fenwick columns of alphabets up to 7 bits in shared memory (66 KB per CTA at 7 bits)
     RDX_CFG(encode_generic_kernel, generic_smem_bytes(kGenericSmemSymbolBits))
     RDX_CFG(decode_generic_kernel, generic_smem_bytes(kGenericSmemSymbolBits))
@@ -176,6 +181,8 @@ struct Plan {
     int cls; uint32_t f, c, tcap; bool wide_table; uint32_t magic_len; uint64_t slot_stride;
     bool aligned = false, full_table = false;   // see LanePlan
     uint64_t gf_m = 0; uint32_t gf_sh = 0;      // see LanePlan
+    int lane_cls = kNarrow;                     // class of the tuned lane kernels (kWideD where the plan allows it)
+    uint64_t gf_m_wide = 0; uint32_t gf_sh_wide = 0;   // frozen reciprocal of the plain WIDE class (warp / split paths)
     // generic path (redux_generic_codec.cuh): symbol_bits != 8 or a pre-trained model
     bool generic = false; uint32_t s = 8, gen_threads = 0, gen_total = 0;
     // byte symbols, code_bits <= 32, model trained before the call: the tuned lane kernels start from its tree
@@ -256,34 +263,43 @@ int make_plan(redux_ctx *ctx, const redux_params_t *p, uint64_t max_block_len, P
     pl->pretrained = ctx->model_freq != nullptr;
     pl->count0 = (uint32_t)total0; pl->eof_freq = ctx->model_freq ? ctx->model_freq[kEof] : 1u;
     const LanePlan lp = lane_plan(p->freq_bits, p->code_bits, max_block_len, pl->count0, pl->pretrained);
-    pl->f = lp.f; pl->c = lp.c; pl->cls = lp.cls; pl->tcap = lp.tcap; pl->wide_table = lp.wide_table;
+    pl->lane_cls = lp.cls;
+    pl->f = lp.f; pl->c = lp.c; pl->cls = lp.cls == kWideD ? (int)kWide : lp.cls; pl->tcap = lp.tcap; pl->wide_table = lp.wide_table;
     pl->magic_len = lp.magic_len; pl->slot_stride = lp.slot_stride;
     pl->aligned = lp.aligned; pl->full_table = lp.full_table;
     pl->gf_m = lp.gf_m; pl->gf_sh = lp.gf_sh;
     return REDUX_OK;
 }
 
+// The reciprocal table the launch will read: the tuned lane kernels of the WIDE_D class divide by double
+// reciprocals, everything else on the same parameters (warp mapping, split encoder) by the 64-bit magics.
+int magic_class(const Plan &pl) { return (pl.lane_cls == kWideD && !pl.warp && !pl.split) ? (int)kWideD : pl.cls; }
+size_t magic_entry_size(int mcls) { return mcls == kNarrow ? sizeof(Magic32) : mcls == kWideD ? sizeof(MagicD) : sizeof(Magic64); }
+
 int get_magic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const Plan &pl, const void **out)
 {
     *out = nullptr;
     if (pl.generic) return REDUX_OK;
-    const uint32_t nbits = pl.cls == kHuge ? 0u : pl.f + pl.c;      // HUGE: one table serves every numerator width
+    const int mcls = magic_class(pl);
+    // HUGE and WIDE_D: one table serves every numerator width
+    const uint32_t nbits = (mcls == kHuge || mcls == kWideD) ? 0u : pl.f + pl.c;
     for (auto &m : d->magics)
-        if (m.cls == pl.cls && m.nbits == nbits && m.len >= pl.magic_len) { *out = m.ptr; return REDUX_OK; }
-    const size_t esz = pl.cls == kNarrow ? sizeof(Magic32) : sizeof(Magic64);
+        if (m.cls == mcls && m.nbits == nbits && m.len >= pl.magic_len) { *out = m.ptr; return REDUX_OK; }
+    const size_t esz = magic_entry_size(mcls);
     // + 64: split_coder_kernel prefetches whole rounds of 32 positions and may index up to 63 entries past the
     // last position it uses (values never consumed, but the reads must stay inside the allocation)
     const uint32_t len = std::max<uint32_t>(pl.magic_len, 1024) + 64;
     void *ptr = nullptr;
     CU_TRY(ctx, cudaMalloc(&ptr, esz * len));
     const uint32_t threads = 256, grid = (len + threads - 1) / threads;
-    if (pl.cls == kNarrow) build_magic_kernel<Magic32><<<grid, threads, 0, stream>>>((Magic32 *)ptr, len, nbits);
-    else                   build_magic_kernel<Magic64><<<grid, threads, 0, stream>>>((Magic64 *)ptr, len, nbits);
+    if (mcls == kNarrow)     build_magic_kernel<Magic32><<<grid, threads, 0, stream>>>((Magic32 *)ptr, len, nbits);
+    else if (mcls == kWideD) build_magic_kernel<MagicD><<<grid, threads, 0, stream>>>((MagicD *)ptr, len, nbits);
+    else                     build_magic_kernel<Magic64><<<grid, threads, 0, stream>>>((Magic64 *)ptr, len, nbits);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     // the table must be visible to work on any stream of this device
     CU_TRY(ctx, cudaStreamSynchronize(stream));
-    d->magics.push_back({pl.cls, nbits, len, ptr});
+    d->magics.push_back({mcls, nbits, len, ptr});
     *out = ptr;
     return REDUX_OK;
 }
@@ -326,7 +342,7 @@ int prepare_generic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const r
 const void *lane_magic(const Plan &pl, const void *magic)
 {
     if (!magic || !pl.pretrained) return magic;
-    const size_t esz = pl.cls == kNarrow ? sizeof(Magic32) : sizeof(Magic64);
+    const size_t esz = magic_entry_size(magic_class(pl));
     return (const uint8_t *)magic + (size_t)(pl.count0 - kNsym) * esz;
 }
 
@@ -365,14 +381,28 @@ void launch_decode_wide(const Plan &pl, const LaneDecJob &job, uint32_t grid, si
     else if (pl.full_table)  decode_lane_al_kernel<uint16_t, kWide, true, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
     else                     decode_lane_al_kernel<uint16_t, kWide, false, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
 }
+template <bool C32>
+void launch_encode_wided(const Plan &pl, const LaneEncJob &job, uint32_t grid, size_t smem, cudaStream_t s)
+{
+    if (pl.full_table) encode_lane_al_kernel<uint16_t, kWideD, true, C32><<<grid, kLaneThreads, smem, s>>>(job);
+    else               encode_lane_al_kernel<uint16_t, kWideD, false, C32><<<grid, kLaneThreads, smem, s>>>(job);
+}
+template <bool C32>
+void launch_decode_wided(const Plan &pl, const LaneDecJob &job, uint32_t grid, size_t smem, cudaStream_t s)
+{
+    if (pl.full_table) decode_lane_al_kernel<uint16_t, kWideD, true, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
+    else               decode_lane_al_kernel<uint16_t, kWideD, false, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
+}
 void launch_encode_al(const Plan &pl, const LaneEncJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {
+    if (pl.lane_cls == kWideD) { if (pl.c == 32) launch_encode_wided<true>(pl, job, grid, smem, s); else launch_encode_wided<false>(pl, job, grid, smem, s); return; }
     if (pl.cls == kNarrow) encode_lane_al_kernel<uint16_t, kNarrow, true, false><<<grid, kLaneThreads, smem, s>>>(job);
     else if (pl.c == 32)   launch_encode_wide<true>(pl, job, grid, smem, s);
     else                   launch_encode_wide<false>(pl, job, grid, smem, s);
 }
 void launch_decode_al(const Plan &pl, const LaneDecJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {
+    if (pl.lane_cls == kWideD) { if (pl.c == 32) launch_decode_wided<true>(pl, job, grid, smem, s); else launch_decode_wided<false>(pl, job, grid, smem, s); return; }
     if (pl.cls == kNarrow) {
         if (pl.c <= 16) decode_lane_al_kernel<uint16_t, kNarrow, true, false, true><<<grid, kLaneThreads, smem, s>>>(job);
         else            decode_lane_al_kernel<uint16_t, kNarrow, true, false, false><<<grid, kLaneThreads, smem, s>>>(job);
@@ -516,6 +546,10 @@ extern "C" int redux_debug_magic(uint64_t d, uint32_t nbits, int wide, uint64_t 
 {
     if (d < 1 || d >> 32) return REDUX_INVALID_INPUT;
     if (wide == 2) { if (d < 2) return REDUX_INVALID_INPUT; Magic64 g = make_magic65(d); *magic = g.m; *shift = g.sh; return REDUX_OK; }
+    if (wide == 3) {
+        if (d >= kWideDMaxCount) return REDUX_INVALID_INPUT;
+        union { double f; uint64_t u; } cv; cv.f = make_magicd((uint32_t)d).r; *magic = cv.u; *shift = 0; return REDUX_OK;
+    }
     if (wide) { if (nbits > 62) return REDUX_INVALID_INPUT; Magic64 g = make_magic64(d, nbits); *magic = g.m; *shift = g.sh; }
     else      { if (nbits > 30) return REDUX_INVALID_INPUT; Magic32 g = make_magic32((uint32_t)d, nbits); *magic = g.m; *shift = g.sh; }
     return REDUX_OK;
@@ -524,6 +558,7 @@ extern "C" int redux_debug_magic(uint64_t d, uint32_t nbits, int wide, uint64_t 
 extern "C" uint64_t redux_debug_magic_divide(uint64_t n, uint64_t magic, uint32_t shift, int wide)
 {
     if (wide == 2) { Magic64 g{magic, shift, 0}; return div_magic65(n, g); }
+    if (wide == 3) { union { double f; uint64_t u; } cv; cv.u = magic; MagicD g; g.r = cv.f; return div_magicd(n, g); }
     if (wide) { Magic64 g{magic, shift, 0}; return div_magic64(n, g); }
     Magic32 g{(uint32_t)magic, shift};
     return div_magic32((uint32_t)n, g);

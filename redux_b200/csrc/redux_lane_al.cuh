@@ -700,7 +700,7 @@ struct LaneDecoderAl {
                 plo = r2 ? p2 : (ra ? pa : plo);
                 I = Im + (r2 ? (uint32_t)(h << 5) : 0u);
             }
-        } else if (count > kQuotientMaxCount) {
+        } else if (CLS == kWide && count > kQuotientMaxCount) {          // (WIDE_D: totals stay below 2^17)
             // 64-bit products, very long streams: the plain product-domain descent
             phi = C::mulr(count - eof_freq, rm1);
             is_eof = X >= phi;

@@ -101,6 +101,22 @@ template <> struct Cls<kWide> {
     }
     static __device__ __forceinline__ M mk(uint64_t m, uint32_t sh) { M g; g.m = m; g.sh = sh; g.pad = 0; return g; }
 };
+template <> struct Cls<kWideD> {
+    using S = uint32_t; using P = uint64_t; using M = MagicD;
+    static __device__ __forceinline__ P mulr(uint32_t v, S rm1) { return (uint64_t)v * rm1 + v; }
+    static __device__ __forceinline__ P mul_add(uint32_t v, S rm1, P acc) { return (uint64_t)v * rm1 + (acc + v); }
+    static __device__ __forceinline__ P divc(P n, const M &g, uint32_t) { return div_magicd(n, g); }
+    static __device__ __forceinline__ M ldm(const M *p) { M g; g.r = __ldg(reinterpret_cast<const double *>(p)); return g; }
+    static __device__ __forceinline__ M mk(uint64_t bits, uint32_t) {
+        M g;
+#if defined(__CUDA_ARCH__)
+        g.r = __longlong_as_double((long long)bits);
+#else
+        union { double d; uint64_t u; } cv; cv.u = bits; g.r = cv.d;
+#endif
+        return g;
+    }
+};
 template <> struct Cls<kHuge> {
     using S = uint64_t; using P = uint64_t; using M = Magic64;
     static __device__ __forceinline__ P mulr(uint32_t v, S rm1) { return (uint64_t)v * rm1 + v; }

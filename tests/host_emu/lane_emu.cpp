@@ -35,6 +35,12 @@ std::vector<uint8_t> build_magic(const LanePlan &pl)
         for (uint32_t i = 0; i < pl.magic_len; ++i) m[i] = make_magic65(kNsym + i);
         return buf;
     }
+    if (pl.cls == kWideD) {
+        buf.resize(sizeof(MagicD) * pl.magic_len);
+        MagicD *m = reinterpret_cast<MagicD *>(buf.data());
+        for (uint32_t i = 0; i < pl.magic_len; ++i) m[i] = make_magicd(kNsym + i);
+        return buf;
+    }
     if (pl.cls == kNarrow) {
         buf.resize(sizeof(Magic32) * pl.magic_len);
         Magic32 *m = reinterpret_cast<Magic32 *>(buf.data());
@@ -60,6 +66,17 @@ void run_grid(K kernel, const J &job, uint64_t n_blocks)
         }
 }
 
+}  // namespace
+
+namespace {
+// the plan without the double-reciprocal class (forced 32-bit tables, the generic kernels)
+void plain_wide(LanePlan &pl)
+{
+    if (pl.cls != kWideD) return;
+    pl.cls = kWide;
+    const Magic64 g = make_magic64(((uint64_t)1 << pl.f) - 1, pl.f + pl.c);
+    pl.gf_m = g.m; pl.gf_sh = g.sh;
+}
 }  // namespace
 
 extern "C" uint64_t emu_slot_stride(uint32_t f, uint32_t c, uint64_t max_block_len)
@@ -89,7 +106,7 @@ LaneStart lane_start(const uint32_t *freq)
 const void *shift_magic(const LanePlan &pl, const std::vector<uint8_t> &magic, uint32_t count0)
 {
     if (magic.empty()) return nullptr;
-    return magic.data() + (size_t)(count0 - kNsym) * (pl.cls == kNarrow ? sizeof(Magic32) : sizeof(Magic64));
+    return magic.data() + (size_t)(count0 - kNsym) * (pl.cls == kNarrow ? sizeof(Magic32) : pl.cls == kWideD ? sizeof(MagicD) : sizeof(Magic64));
 }
 }  // namespace
 
@@ -102,6 +119,7 @@ extern "C" int emu_encode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len
     const bool legacy = force_wide_table >= 2;            // 2/3: the generic kernels of redux_lane_codec.cuh
     if (force_wide_table >= 2) force_wide_table -= 2;
     if (force_wide_table >= 0) { pl.wide_table = force_wide_table != 0; if (pl.wide_table) pl.full_table = true; }
+    if (legacy || pl.wide_table) plain_wide(pl);
     std::vector<uint8_t> magic = build_magic(pl);
     LaneEncJob job;
     job.in = in; job.in_off = in_off; job.n_blocks = n_blocks;
@@ -115,7 +133,9 @@ extern "C" int emu_encode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len
      pl.cls == kWide   ? run_grid(encode_lane_kernel<TW, kWide>, job, n_blocks)   : \
                          run_grid(encode_lane_kernel<TW, kHuge>, job, n_blocks))
 #define RUN_AL(TW, FULL) \
-    (pl.cls == kNarrow ? run_grid(encode_lane_al_kernel<TW, kNarrow, FULL, false>, job, n_blocks) : \
+    (pl.cls == kWideD && pl.c == 32 ? run_grid(encode_lane_al_kernel<uint16_t, kWideD, FULL, true>, job, n_blocks) : \
+     pl.cls == kWideD  ? run_grid(encode_lane_al_kernel<uint16_t, kWideD, FULL, false>, job, n_blocks) : \
+     pl.cls == kNarrow ? run_grid(encode_lane_al_kernel<TW, kNarrow, FULL, false>, job, n_blocks) : \
      pl.c == 32        ? run_grid(encode_lane_al_kernel<TW, kWide, FULL, true>, job, n_blocks) : \
                          run_grid(encode_lane_al_kernel<TW, kWide, FULL, false>, job, n_blocks))
     if (pl.aligned && !legacy) {
@@ -145,6 +165,7 @@ extern "C" int emu_decode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len
     const bool legacy = force_wide_table >= 2;            // 2/3: the generic kernels of redux_lane_codec.cuh
     if (force_wide_table >= 2) force_wide_table -= 2;
     if (force_wide_table >= 0) { pl.wide_table = force_wide_table != 0; if (pl.wide_table) pl.full_table = true; }
+    if (legacy || pl.wide_table) plain_wide(pl);
     std::vector<uint8_t> magic = build_magic(pl);
     LaneDecJob job;
     job.comp = comp; job.comp_off = comp_off; job.n_blocks = n_blocks;
@@ -158,7 +179,9 @@ extern "C" int emu_decode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len
      pl.cls == kWide   ? run_grid(decode_lane_kernel<TW, kWide>, job, n_blocks)   : \
                          run_grid(decode_lane_kernel<TW, kHuge>, job, n_blocks))
 #define RUN_AL(TW, FULL) \
-    (pl.cls == kNarrow && pl.c <= 16 ? run_grid(decode_lane_al_kernel<TW, kNarrow, FULL, false, true>, job, n_blocks) : \
+    (pl.cls == kWideD && pl.c == 32 ? run_grid(decode_lane_al_kernel<uint16_t, kWideD, FULL, true, false>, job, n_blocks) : \
+     pl.cls == kWideD  ? run_grid(decode_lane_al_kernel<uint16_t, kWideD, FULL, false, false>, job, n_blocks) : \
+     pl.cls == kNarrow && pl.c <= 16 ? run_grid(decode_lane_al_kernel<TW, kNarrow, FULL, false, true>, job, n_blocks) : \
      pl.cls == kNarrow ? run_grid(decode_lane_al_kernel<TW, kNarrow, FULL, false, false>, job, n_blocks) : \
      pl.c == 32        ? run_grid(decode_lane_al_kernel<TW, kWide, FULL, true, false>, job, n_blocks) : \
                          run_grid(decode_lane_al_kernel<TW, kWide, FULL, false, false>, job, n_blocks))
