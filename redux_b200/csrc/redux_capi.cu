@@ -164,11 +164,13 @@ cudaError_t configure_kernels()
     RDX_CFG((encode_lane_al_kernel<uint32_t, kWide, true, C32>), s32)  RDX_CFG((decode_lane_al_kernel<uint32_t, kWide, true, C32, false>), s32)
     RDX_CFG_WIDE(false) RDX_CFG_WIDE(true)
 #undef RDX_CFG_WIDE
-    // WIDE_D (double-reciprocal division; 16-bit tables only, redux_common.cuh MagicD)
+    // WIDE_D (double-reciprocal division, redux_common.cuh MagicD)
 #define RDX_CFG_WIDED(FULL, C32) \
     RDX_CFG((encode_lane_al_kernel<uint16_t, kWideD, FULL, C32>), s16) RDX_CFG((decode_lane_al_kernel<uint16_t, kWideD, FULL, C32, false>), s16)
     RDX_CFG_WIDED(true, false) RDX_CFG_WIDED(true, true) RDX_CFG_WIDED(false, false) RDX_CFG_WIDED(false, true)
 #undef RDX_CFG_WIDED
+    RDX_CFG((encode_lane_al_kernel<uint32_t, kWideD, true, false>), s32) RDX_CFG((decode_lane_al_kernel<uint32_t, kWideD, true, false, false>), s32)
+    RDX_CFG((encode_lane_al_kernel<uint32_t, kWideD, true, true>), s32)  RDX_CFG((decode_lane_al_kernel<uint32_t, kWideD, true, true, false>), s32)
     // generic kernels: Fenwick columns of alphabets up to 7 bits in shared memory (66 KB per CTA at 7 bits)
     RDX_CFG(encode_generic_kernel, generic_smem_bytes(kGenericSmemSymbolBits))
     RDX_CFG(decode_generic_kernel, generic_smem_bytes(kGenericSmemSymbolBits))
@@ -384,14 +386,16 @@ void launch_decode_wide(const Plan &pl, const LaneDecJob &job, uint32_t grid, si
 template <bool C32>
 void launch_encode_wided(const Plan &pl, const LaneEncJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {
-    if (pl.full_table) encode_lane_al_kernel<uint16_t, kWideD, true, C32><<<grid, kLaneThreads, smem, s>>>(job);
-    else               encode_lane_al_kernel<uint16_t, kWideD, false, C32><<<grid, kLaneThreads, smem, s>>>(job);
+    if (pl.wide_table)      encode_lane_al_kernel<uint32_t, kWideD, true, C32><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (pl.full_table) encode_lane_al_kernel<uint16_t, kWideD, true, C32><<<grid, kLaneThreads, smem, s>>>(job);
+    else                    encode_lane_al_kernel<uint16_t, kWideD, false, C32><<<grid, kLaneThreads, smem, s>>>(job);
 }
 template <bool C32>
 void launch_decode_wided(const Plan &pl, const LaneDecJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {
-    if (pl.full_table) decode_lane_al_kernel<uint16_t, kWideD, true, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
-    else               decode_lane_al_kernel<uint16_t, kWideD, false, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
+    if (pl.wide_table)      decode_lane_al_kernel<uint32_t, kWideD, true, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
+    else if (pl.full_table) decode_lane_al_kernel<uint16_t, kWideD, true, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
+    else                    decode_lane_al_kernel<uint16_t, kWideD, false, C32, false><<<grid, kLaneThreads, smem, s>>>(job);
 }
 void launch_encode_al(const Plan &pl, const LaneEncJob &job, uint32_t grid, size_t smem, cudaStream_t s)
 {

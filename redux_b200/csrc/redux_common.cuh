@@ -24,7 +24,7 @@ constexpr uint32_t kNsym = 257;         // Parameters::symbol_count (src/model/m
 //   WIDE  : code <= 32      -> 32-bit coder state, 64-bit products, 64-bit magic division.
 //   HUGE  : code  > 32      -> 64-bit coder state, products < 2^64 (code+freq <= 64), hardware-less
 //                              64-bit division (rare parameter corner; correctness only).
-//   WIDE_D: WIDE whose totals stay below 2^17 for the whole launch (e.g. any 64 KiB block of a fresh model): the
+//   WIDE_D: WIDE whose totals stay below 349,525 for the whole launch (e.g. any 64 KiB block of a fresh model): the
 //           two divisions by the total become one double-precision multiply-add each (lane_plan decides).
 enum ArithClass { kNarrow = 0, kWide = 1, kHuge = 2, kWideD = 3 };
 
@@ -114,20 +114,21 @@ RDX_HD uint64_t div_magic65(uint64_t n, Magic64 g) {
     return (((n - t) >> 1) + t) >> (g.sh - 1);
 }
 
-// WIDE_D: floor(n / d) for n = cum * range < 2^49 (cum <= d < 2^17, range <= 2^32) as trunc(fma(n, r, 2^-18)) with
-// r = the double nearest to 1/d.  n and d are exact doubles; |n r - n/d| <= (n/d) 2^-53 <= 2^-21 and the rounding of
-// the fused result adds at most another 2^-21, so the computed value lies within E = 2^-20 of n/d + 2^-18.  If d divides
-// n the result is >= k + 2^-18 - E > k; otherwise n/d is at least 1/d > 2^-17 below the next integer and
-// 2^-18 + E < 2^-17 keeps the result below it: the truncation is the exact quotient, no correction step.
+// WIDE_D: floor(n / d) for n = cum * range (cum <= d, range <= 2^32) as trunc(fma(n, r, 2^-19)) with r = the double
+// nearest to 1/d, valid for every total d < 349,525 (= 2^19 / 1.5).  n < 2^51 and d are exact doubles;
+// |n r - n/d| <= (n/d) 2^-53 <= 2^-21 and the rounding of the fused result (magnitude <= 2^32) adds at most another
+// 2^-21, so the computed value lies within E = 2^-20 of n/d + 2^-19.  If d divides n the result is >= k + 2^-19 - E > k;
+// otherwise n/d is at least 1/d below the next integer and 2^-19 + E = 1.5 x 2^-19 < 1/d keeps the result below it:
+// the truncation is the exact quotient, no correction step.
 // (The conversion goes through 64 bits: the quotient reaches 2^32 when cum == d and range == 2^32.)
 struct MagicD { double r; };
-constexpr uint32_t kWideDMaxCount = 1u << 17;                 // totals must stay BELOW this
+constexpr uint32_t kWideDMaxCount = 349525;                   // totals must stay BELOW this
 RDX_HD MagicD make_magicd(uint32_t d) { MagicD g; g.r = 1.0 / (double)d; return g; }
 RDX_HD uint64_t div_magicd(uint64_t n, MagicD g) {
 #if defined(__CUDA_ARCH__)
-    return __double2ull_rz(fma(__ull2double_rn(n), g.r, 0x1p-18));
+    return __double2ull_rz(fma(__ull2double_rn(n), g.r, 0x1p-19));
 #else
-    return (uint64_t)__builtin_fma((double)n, g.r, 0x1p-18);
+    return (uint64_t)__builtin_fma((double)n, g.r, 0x1p-19);
 #endif
 }
 
@@ -214,8 +215,8 @@ RDX_HD LanePlan lane_plan(uint32_t f, uint32_t c, uint64_t max_block_len, uint32
     pl.slot_stride = ((bound + 15) & ~(uint64_t)15) + 16;
     pl.aligned = pl.cls != kHuge;
     pl.full_table = pretrained || pl.wide_table || updates + 256 <= 65535;   // cum(i) <= 256 + updates must fit u16
-    // 16-bit tables + every total of the launch below 2^17: the double-reciprocal division (see MagicD)
-    if (pl.cls == kWide && !pl.wide_table && (uint64_t)count0 + updates < kWideDMaxCount) pl.cls = kWideD;
+    // every total of the launch below the bound: the double-reciprocal division (see MagicD)
+    if (pl.cls == kWide && (uint64_t)count0 + updates < kWideDMaxCount) pl.cls = kWideD;
     pl.gf_m = 0; pl.gf_sh = 0;
     if (pl.cls == kNarrow)    { const Magic32 g = make_magic32((uint32_t)fmax, f + c); pl.gf_m = g.m; pl.gf_sh = g.sh; }
     else if (pl.cls == kWide) { const Magic64 g = make_magic64(fmax, f + c); pl.gf_m = g.m; pl.gf_sh = g.sh; }

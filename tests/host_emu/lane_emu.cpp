@@ -119,7 +119,7 @@ extern "C" int emu_encode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len
     const bool legacy = force_wide_table >= 2;            // 2/3: the generic kernels of redux_lane_codec.cuh
     if (force_wide_table >= 2) force_wide_table -= 2;
     if (force_wide_table >= 0) { pl.wide_table = force_wide_table != 0; if (pl.wide_table) pl.full_table = true; }
-    if (legacy || pl.wide_table) plain_wide(pl);
+    if (legacy) plain_wide(pl);
     std::vector<uint8_t> magic = build_magic(pl);
     LaneEncJob job;
     job.in = in; job.in_off = in_off; job.n_blocks = n_blocks;
@@ -133,8 +133,8 @@ extern "C" int emu_encode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len
      pl.cls == kWide   ? run_grid(encode_lane_kernel<TW, kWide>, job, n_blocks)   : \
                          run_grid(encode_lane_kernel<TW, kHuge>, job, n_blocks))
 #define RUN_AL(TW, FULL) \
-    (pl.cls == kWideD && pl.c == 32 ? run_grid(encode_lane_al_kernel<uint16_t, kWideD, FULL, true>, job, n_blocks) : \
-     pl.cls == kWideD  ? run_grid(encode_lane_al_kernel<uint16_t, kWideD, FULL, false>, job, n_blocks) : \
+    (pl.cls == kWideD && pl.c == 32 ? run_grid(encode_lane_al_kernel<TW, kWideD, FULL, true>, job, n_blocks) : \
+     pl.cls == kWideD  ? run_grid(encode_lane_al_kernel<TW, kWideD, FULL, false>, job, n_blocks) : \
      pl.cls == kNarrow ? run_grid(encode_lane_al_kernel<TW, kNarrow, FULL, false>, job, n_blocks) : \
      pl.c == 32        ? run_grid(encode_lane_al_kernel<TW, kWide, FULL, true>, job, n_blocks) : \
                          run_grid(encode_lane_al_kernel<TW, kWide, FULL, false>, job, n_blocks))
@@ -165,7 +165,7 @@ extern "C" int emu_decode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len
     const bool legacy = force_wide_table >= 2;            // 2/3: the generic kernels of redux_lane_codec.cuh
     if (force_wide_table >= 2) force_wide_table -= 2;
     if (force_wide_table >= 0) { pl.wide_table = force_wide_table != 0; if (pl.wide_table) pl.full_table = true; }
-    if (legacy || pl.wide_table) plain_wide(pl);
+    if (legacy) plain_wide(pl);
     std::vector<uint8_t> magic = build_magic(pl);
     LaneDecJob job;
     job.comp = comp; job.comp_off = comp_off; job.n_blocks = n_blocks;
@@ -179,8 +179,8 @@ extern "C" int emu_decode_lane_ex(uint32_t f, uint32_t c, uint64_t max_block_len
      pl.cls == kWide   ? run_grid(decode_lane_kernel<TW, kWide>, job, n_blocks)   : \
                          run_grid(decode_lane_kernel<TW, kHuge>, job, n_blocks))
 #define RUN_AL(TW, FULL) \
-    (pl.cls == kWideD && pl.c == 32 ? run_grid(decode_lane_al_kernel<uint16_t, kWideD, FULL, true, false>, job, n_blocks) : \
-     pl.cls == kWideD  ? run_grid(decode_lane_al_kernel<uint16_t, kWideD, FULL, false, false>, job, n_blocks) : \
+    (pl.cls == kWideD && pl.c == 32 ? run_grid(decode_lane_al_kernel<TW, kWideD, FULL, true, false>, job, n_blocks) : \
+     pl.cls == kWideD  ? run_grid(decode_lane_al_kernel<TW, kWideD, FULL, false, false>, job, n_blocks) : \
      pl.cls == kNarrow && pl.c <= 16 ? run_grid(decode_lane_al_kernel<TW, kNarrow, FULL, false, true>, job, n_blocks) : \
      pl.cls == kNarrow ? run_grid(decode_lane_al_kernel<TW, kNarrow, FULL, false, false>, job, n_blocks) : \
      pl.c == 32        ? run_grid(decode_lane_al_kernel<TW, kWide, FULL, true, false>, job, n_blocks) : \

@@ -115,13 +115,14 @@ def test_count_reciprocal_65_bit_is_exact_for_every_64_bit_numerator():
             assert L.redux_debug_magic_divide(int(n), m, sh, 2) == int(n) // d, (n, d)
 
 
-def test_count_reciprocal_double_is_exact_below_2_17():
-    """WIDE_D: floor(cum * range / d) as trunc(fma(n, 1/d, 2^-18)) for every total d < 2^17, cum <= d, range <= 2^32 --
-    exact multiples, their predecessors (the cases a rounding error could tip) and random products."""
+def test_count_reciprocal_double_is_exact_below_its_bound():
+    """WIDE_D: floor(cum * range / d) as trunc(fma(n, 1/d, 2^-19)) for every total d < 349,525, cum <= d,
+    range <= 2^32 -- exact multiples, their neighbours (the cases a rounding error could tip) and random products."""
     rng = np.random.default_rng(17)
     L = rb.lib()
-    ds = [257, 258, 511, 512, 513, 4095, 4096, 65535, 65536, 65537, 65793, (1 << 17) - 1, (1 << 17) - 2, 98765]
-    ds += [int(x) for x in rng.integers(257, 1 << 17, size=150)]
+    top = 349525
+    ds = [257, 258, 511, 512, 513, 4095, 4096, 65535, 65536, 65537, 65793, (1 << 17) - 1, 1 << 17, (1 << 18) + 1, top - 1, top - 2, 98765]
+    ds += [int(x) for x in rng.integers(257, top, size=150)]
     ranges = [1 << 32, (1 << 32) - 1, (1 << 31) + 1, 1 << 24, (1 << 30) + 2, 3, 2]
     for d in ds:
         m, sh = _magic(d, 0, 3)
@@ -130,10 +131,10 @@ def test_count_reciprocal_double_is_exact_below_2_17():
             for cum in cums:
                 n = cum * r
                 assert L.redux_debug_magic_divide(n, m, sh, 3) == n // d, (n, d)
-        for k in [int(x) for x in rng.integers(1, (1 << 49) // d, size=200, dtype=np.uint64)]:      # multiples and predecessors
-            for n in (k * d, k * d - 1, k * d + 1):
+        for k in [int(x) for x in rng.integers(1, 1 << 32, size=200, dtype=np.uint64)] + [(1 << 32) - 1, 1 << 32]:
+            for n in (k * d, k * d - 1, k * d + 1):                      # multiples and their neighbours, quotients up to 2^32
                 assert L.redux_debug_magic_divide(n, m, sh, 3) == n // d, (n, d)
-    assert _bad_magic((1 << 17), 3)
+    assert _bad_magic(top, 3)
 
 
 def _bad_magic(d, wide):
