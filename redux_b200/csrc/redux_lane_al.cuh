@@ -728,13 +728,12 @@ struct LaneDecoderAl {
         } else {
             // 64-bit products: get the reference's value = X / range (src/codec.rs:131) FIRST -- a float
             // estimate made exact by one remainder check -- and search in the 32-bit value domain, two
-            // tree levels per round like the narrow class.  The estimate is within one of the quotient
-            // because the quotient is < count <= 2^20: relative error 2^-24 (X) + 2^-24 (range) + 2^-23
-            // (MUFU.RCP) + 2^-24 (product) keeps the absolute error below 0.4.
-            uint32_t v = (uint32_t)(__ull2float_rn((unsigned long long)X) * rcp_approx((float)rm1 + 1.0f));
-            const P pv = C::mulr(v, rm1);                     // v * range
-            if (pv > X) v -= 1u;                              // estimate one too high
-            else if (X - pv > (P)rm1) v += 1u;                // one too low (remainder >= range)
+            // tree levels per round like the narrow class.  The quotient is < count <= 2^20, so the relative
+            // errors 2^-24 (X) + 2 x 2^-24 (range) + 2^-23 (MUFU.RCP) + 2^-24 (product) keep the estimate within
+            // 0.375 of X / range; biased down by 0.4 its truncation is the quotient or one less (never more, never
+            // negative beyond -0.775, which truncates to 0), so ONE one-sided check finishes it.
+            uint32_t v = (uint32_t)fmaf(__ull2float_rn((unsigned long long)X), rcp_approx((float)rm1 + 1.0f), -0.4f);
+            if (X - C::mulr(v, rm1) > (P)rm1) v += 1u;         // remainder >= range: the estimate was one too low
             uint32_t lo = 0, hi = count - eof_freq;           // cum(i) <= v < hi tracked in the value domain
             is_eof = v >= hi;                                 // the quotient is in hand: no product for node 256
 #pragma unroll

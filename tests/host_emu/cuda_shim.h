@@ -5,6 +5,7 @@
 // without a GPU check every change to the kernels against the oracle before GPU minutes are spent.
 // It is never linked into libredux_b200.so: the product has no CPU path.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 
