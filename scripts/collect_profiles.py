@@ -54,7 +54,7 @@ def loops(listing):
 
 
 for kern, name in (("decode_lane_al_kernelItLi0ELb1ELb0ELb1", "decode_narrow"), ("encode_lane_al_kernelItLi0ELb1ELb0", "encode_narrow"),
-                   ("decode_lane_al_kernelItLi1ELb0ELb1ELb0", "decode_wide_c32"), ("encode_lane_al_kernelItLi1ELb0ELb1", "encode_wide_c32")):
+                   ("decode_lane_al_kernelItLi3ELb0ELb1ELb0", "decode_wide_d_c32"), ("encode_lane_al_kernelItLi3ELb0ELb1", "encode_wide_d_c32")):
     lst = run(sys.executable, "scripts/sass_ctl.py", kern).stdout
     lines, lp = loops(lst)
     big = sorted((b - a, a, b) for a, b in lp if b - a > 200)[-2:]        # the adaptive and the frozen main loops
