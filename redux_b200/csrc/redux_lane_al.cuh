@@ -224,7 +224,7 @@ struct BitSink2 {
     __device__ __forceinline__ uint32_t put_code(uint32_t bits, uint32_t n1, uint32_t pend, uint32_t k) {
         const bool emit = n1 != 0;
         const uint32_t n = emit ? n1 + pend : 0u;
-        if (n > 32) {                                                       // rare: long E3 run
+        if (__builtin_expect(n > 32, 0)) {                                  // rare: long E3 run
             const uint32_t b = (bits >> (n1 - 1)) & 1u;
             put(b, 1);
             while (pend > 0) {

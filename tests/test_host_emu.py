@@ -389,6 +389,25 @@ def test_wide_decoder_quotient_estimate_and_its_fallback(emu):
         assert int(status[0]) == 0 and outs[0] == big and int(consumed[0]) == len(want)
 
 
+def test_double_reciprocal_class_and_its_boundary(emu):
+    """WIDE_D (totals below 349,525 for the whole launch: the two divisions by the total are one double-precision
+    multiply-add each) against the oracle, on both sides of the bound: a block of 349,267 symbols keeps every total
+    below it (257 + 349,267 = 349,524; 32-bit tables), one more symbol switches the launch to the 64-bit magics.  The
+    quotient 2^32 (cum == total at full range, c = 32) and totals around 2^16 / 2^17 / 2^18 are all on this path."""
+    rng = np.random.default_rng(349525)
+    for L in (349267, 349268):
+        blk = np.concatenate([rng.integers(0, 256, L // 3, dtype=np.uint8),
+                              np.full(L // 3, 255, dtype=np.uint8),                    # symbol 255: cum_hi reaches cum(256)
+                              np.minimum(rng.geometric(0.4, L - 2 * (L // 3)) - 1, 255).astype(np.uint8)]).tobytes()
+        assert len(blk) == L
+        for f, c in ((30, 32), (22, 24), (19, 21)):
+            rc, want, ic, oc = o.compress(blk, o.TREE, (8, f, c))
+            assert rc == o.OK
+            assert emu_encode(emu, [blk, b"redux"], f, c)[0] == want, (L, f, c)
+            outs, raw_len, consumed, status = emu_decode(emu, [want], [L + 1], f, c)
+            assert int(status[0]) == 0 and outs[0] == blk and int(consumed[0]) == len(want), (L, f, c)
+
+
 def test_kernels_equal_the_golden_vectors(emu):
     """Every committed golden vector (tests/golden/make_golden.py: an independent second reading of the
     reference, incl. odd symbol widths and models trained before the call) through the kernels that would
