@@ -825,22 +825,24 @@ struct LaneDecoderAl {
                 m0 = C::ldm(magic + t + 4); m1 = C::ldm(magic + t + 5); m2 = C::ldm(magic + t + 6); m3 = C::ldm(magic + t + 7);
             }
             constexpr int M1 = STG ? 1 : 0, M2 = STG ? 2 : 0;     // pairs of steps share one refill point
+            // a step that ends the stream (st != 0 from then on) leaves through `break`: both loops and the code
+            // after them converge in one place, so the exits need one convergence scope, not two
             uint32_t wv;
-            if (!step<ADAPT, false, M1>(sym, g0, count_frozen)) return;
+            if (!step<ADAPT, false, M1>(sym, g0, count_frozen)) break;
             wv = sym;
-            if (!step<ADAPT, false, M2>(sym, g1, count_frozen)) { out.partial(wv, 1); return; }
+            if (!step<ADAPT, false, M2>(sym, g1, count_frozen)) { out.partial(wv, 1); break; }
             wv |= sym << 8;
-            if (!step<ADAPT, false, M1>(sym, g2, count_frozen)) { out.partial(wv, 2); return; }
+            if (!step<ADAPT, false, M1>(sym, g2, count_frozen)) { out.partial(wv, 2); break; }
             wv |= sym << 16;
-            if (!step<ADAPT, false, M2>(sym, g3, count_frozen)) { out.partial(wv, 3); return; }
+            if (!step<ADAPT, false, M2>(sym, g3, count_frozen)) { out.partial(wv, 3); break; }
             out.put4(wv | (sym << 24));
             if (ADAPT) { g0 = m0; g1 = m1; g2 = m2; g3 = m3; }
         }
         M gn = g0;
-        while (t < t_end) {
+        while (st == 0 && t < t_end) {
             const M g = gn;
             if (ADAPT) gn = C::ldm(magic + t + 1);
-            if (!step<ADAPT, false>(sym, g, count_frozen)) return;
+            if (!step<ADAPT, false>(sym, g, count_frozen)) break;
             out.put(sym);
         }
         if (ADAPT) { tab.t[128 << 5] = (TW)top_a; tab.t[64 << 5] = (TW)top_b; tab.t[192 << 5] = (TW)top_c; }
