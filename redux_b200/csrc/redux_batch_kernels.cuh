@@ -23,12 +23,13 @@ template <> struct MagicMaker<MagicD> {
     static __device__ MagicD make(uint32_t d, uint32_t) { return make_magicd(d); }
 };
 
-// out[tt] = magic of count 257 + tt for numerators < 2^nbits
+// out[tt] = magic of count first + tt for numerators < 2^nbits (first = 257, the fresh byte model's total, for the
+// lane kernels; the start total of the call for the generic kernels)
 template <typename M>
-__global__ void build_magic_kernel(M *out, uint32_t n, uint32_t nbits)
+__global__ void build_magic_kernel(M *out, uint32_t n, uint32_t nbits, uint32_t first = kNsym)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = MagicMaker<M>::make(kNsym + i, nbits);
+    if (i < n) out[i] = MagicMaker<M>::make(first + i, nbits);
 }
 
 // ---------------------------------------------------------------------------------------------

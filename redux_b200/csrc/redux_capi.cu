@@ -86,7 +86,7 @@ struct DeviceState {
     DevBuf slots, sizes, flag;                 // encoder workspace
     DevBuf st_in, st_off, st_out, st_ooff, st_status, st_aux0, st_aux1, st_roff;   // host-API staging
     DevBuf split_hist, split_pairs;            // split encoder: chunk histograms, per-position ranges
-    DevBuf gen_tabs, gen_init, gen_freq;       // generic path: Fenwick columns, start tree, uploaded frequencies
+    DevBuf gen_tabs, gen_init, gen_freq, gen_magic;   // generic path: Fenwick columns, start tree, uploaded frequencies, reciprocals
     uint8_t *text_lut = nullptr;
     DevBuf corpus; uint64_t corpus_len = 0;    // text-class corpus of the synthetic generator (redux_ctx_set_text_corpus)
     std::vector<MagicEntry> magics;
@@ -190,6 +190,7 @@ struct Plan {
     // byte symbols, code_bits <= 32, model trained before the call: the tuned lane kernels start from its tree
     bool pretrained = false; uint32_t count0 = kNsym, eof_freq = 1;
     uint32_t *gen_tabs = nullptr; const uint32_t *gen_init = nullptr;
+    const Magic64 *gen_magic = nullptr; uint32_t gen_magic_len = 0;
     bool warp = false;      // one stream per warp (latency mapping) instead of one per lane
     bool split = false;     // encode only: parallel model phase + one-warp coder chain (redux_split_encoder.cuh)
     uint64_t max_len = 0;   // longest block of the launch
@@ -327,6 +328,18 @@ int prepare_generic(redux_ctx *ctx, DeviceState *d, cudaStream_t stream, const r
         CU_TRY(ctx, cudaStreamSynchronize(stream));
         return REDUX_OK;
     }
+    // reciprocals of every total a block of this call can reach: init_total .. min(freq_max, init_total + symbols)
+    {
+        const uint64_t fmax = ((uint64_t)1 << p->freq_bits) - 1;
+        const uint64_t syms = pl->max_len * 8 / p->symbol_bits + 1;                     // data symbols + EOF
+        const uint64_t top = std::min<uint64_t>(fmax, (uint64_t)pl->gen_total + syms);
+        const uint32_t len = (uint32_t)(top - pl->gen_total + 2);
+        CU_TRY(ctx, d->gen_magic.reserve((size_t)len * sizeof(Magic64)));
+        build_magic_kernel<Magic64><<<(len + 255) / 256, 256, 0, stream>>>((Magic64 *)d->gen_magic.p, len, 0u, pl->gen_total);
+        ctx->launches++;
+        CU_TRY(ctx, cudaGetLastError());
+        pl->gen_magic = (const Magic64 *)d->gen_magic.p; pl->gen_magic_len = len;
+    }
     const uint64_t col_bytes = (uint64_t)(nsym + 1) * sizeof(uint32_t);
     uint64_t threads = std::min<uint64_t>((n_blocks + kGenericThreads - 1) / kGenericThreads * kGenericThreads,
                                           (uint64_t)148 * 16 * kGenericThreads);
@@ -353,6 +366,7 @@ GenericJob generic_job(const Plan &pl)
     GenericJob g{};
     g.tabs = pl.gen_tabs; g.init_tree = pl.gen_init; g.init_total = pl.gen_total;
     g.s = pl.s; g.f = pl.f; g.c = pl.c; g.n_threads = pl.gen_threads;
+    g.magic = pl.gen_magic; g.magic_len = pl.gen_magic_len;
     return g;
 }
 
@@ -711,7 +725,7 @@ extern "C" void redux_ctx_destroy(redux_ctx_t *ctx)
         for (int i = 0; i < kPipeStreams; ++i) if (d.pipe[i]) cudaStreamDestroy(d.pipe[i]);
         for (HostBuf *b : {&d.pin_off, &d.pin_status, &d.pin_aux0, &d.pin_aux1}) b->release();
         for (DevBuf *b : {&d.slots, &d.sizes, &d.flag, &d.st_in, &d.st_off, &d.st_out, &d.st_ooff,
-                          &d.st_status, &d.st_aux0, &d.st_aux1, &d.st_roff, &d.corpus, &d.gen_tabs, &d.gen_init, &d.gen_freq, &d.split_hist, &d.split_pairs}) b->release();
+                          &d.st_status, &d.st_aux0, &d.st_aux1, &d.st_roff, &d.corpus, &d.gen_magic, &d.gen_tabs, &d.gen_init, &d.gen_freq, &d.split_hist, &d.split_pairs}) b->release();
         for (auto &m : d.magics) cudaFree(m.ptr);
         if (d.text_lut) cudaFree(d.text_lut);
     }

@@ -8,8 +8,8 @@
 //     is consumed and dropped (it becomes EOF, src/codec.rs:106-110), and the decoder writes symbols with
 //     BitWriter::write_bits but never flushes (src/codec.rs:164-176), so trailing bits that do not fill
 //     a byte are lost -- both quirks of the reference are reproduced, not repaired;
-//   * any code_bits (64-bit coder state, plain 64-bit division: products stay below 2^64 because
-//     code_bits + freq_bits <= 64, src/model/mod.rs:64);
+//   * any code_bits (64-bit coder state; products stay below 2^64 because code_bits + freq_bits <= 64,
+//     src/model/mod.rs:64; the divisions by the total use the 65-bit magic of redux_common.cuh);
 //   * with those, a model that was TRAINED before compress()/decompress() received it (trained byte models
 //     with code_bits <= 32 run on the tuned kernels): the reference takes a
 //     Box<Model> (src/lib.rs:102) whose get_frequency() has possibly been called already
@@ -49,7 +49,20 @@ struct GenericJob {
     uint32_t init_total;        // its total frequency
     uint32_t s, f, c;
     uint32_t n_threads;
+    // 65-bit reciprocals (redux_common.cuh, make_magic65) of the totals init_total .. init_total + magic_len - 1: the
+    // total is a function of the position only, so the two divisions by it (src/codec.rs:59-60 / :133-134) are two
+    // multiplications; the decoder's division by the range (:131) stays a division
+    const Magic64 *magic; uint32_t magic_len;
 };
+
+// reciprocal of the total `count` (init_total <= count < init_total + magic_len by construction of the table)
+__device__ __forceinline__ Magic64 generic_magic(const GenericJob &job, uint32_t count) {
+    uint32_t i = count - job.init_total;
+    if (i >= job.magic_len) i = job.magic_len - 1;      // only if the caller's max_block_len understated a block: stay in bounds
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(job.magic + i));
+    Magic64 g; g.m = ((uint64_t)v.y << 32) | v.x; g.sh = v.z; g.pad = 0;
+    return g;
+}
 
 // The reference's AdaptiveTreeModel over one column of `tabs`.
 struct GenericTree {
@@ -131,8 +144,9 @@ encode_generic_kernel(const GenericJob job)
             const uint64_t cl = tree.prefix(sym), ch = tree.prefix(sym + 1);
             tree.update(sym);
             const uint64_t range = high - low + 1;           // :58 (2^64 cannot occur: c <= 61)
-            const uint64_t h2 = low + range * ch / count - 1;
-            const uint64_t l2 = low + range * cl / count;
+            const Magic64 g = generic_magic(job, (uint32_t)count);
+            const uint64_t h2 = low + div_magic65(range * ch, g) - 1;
+            const uint64_t l2 = low + div_magic65(range * cl, g);
             const Renorm<uint64_t> r = renorm<uint64_t>(l2, h2, c);
             if (r.n1) { sink.put_code(l2 >> (c - r.n1), r.n1, pend); pend = r.k; }
             else pend += r.k;
@@ -180,8 +194,9 @@ decode_generic_kernel(const GenericJob job)
             const uint64_t cl = tree.prefix(sym), ch = tree.prefix(sym + 1);
             if (v >= ch) { st = 2; break; }                   // get_symbol's InvalidInput (unreachable, kept)
             tree.update(sym);
-            high = low + range * ch / count - 1;              // :133-134
-            low = low + range * cl / count;
+            const Magic64 g = generic_magic(job, (uint32_t)count);
+            high = low + div_magic65(range * ch, g) - 1;      // :133-134
+            low = low + div_magic65(range * cl, g);
             if (sym == tree.eof) break;                       // :136-138
             const Renorm<uint64_t> r = renorm<uint64_t>(low, high, c);
             const uint32_t n = r.n1 + r.k;

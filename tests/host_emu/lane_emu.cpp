@@ -3,6 +3,7 @@
 // Built by tests/test_host_emu.py with g++; compared there against the oracle.  Not part of the product.
 #include "cuda_shim.h"
 
+#include <algorithm>
 #include <vector>
 
 thread_local EmuIdx threadIdx, blockIdx, blockDim, gridDim;
@@ -229,9 +230,10 @@ extern "C" uint32_t emu_step_al(uint32_t c, uint32_t f, uint32_t low, uint32_t h
 
 // ------------------------------------------------------------------ generic path (any symbol width, pre-trained models)
 namespace {
-struct GenericSetup { std::vector<uint32_t> init, tabs; GenericJob job; };
+struct GenericSetup { std::vector<uint32_t> init, tabs; std::vector<Magic64> magic; GenericJob job; };
 
-void generic_setup(GenericSetup &g, uint32_t s, uint32_t f, uint32_t c, const uint32_t *freq, uint32_t n_threads)
+void generic_setup(GenericSetup &g, uint32_t s, uint32_t f, uint32_t c, const uint32_t *freq, uint32_t n_threads,
+                   uint64_t max_bytes)
 {
     const uint32_t nsym = (1u << s) + 1;
     g.init.assign(nsym + 1, 0);
@@ -244,6 +246,12 @@ void generic_setup(GenericSetup &g, uint32_t s, uint32_t f, uint32_t c, const ui
     g.job = GenericJob{};
     g.job.tabs = g.tabs.data(); g.job.init_tree = g.init.data(); g.job.init_total = (uint32_t)total;
     g.job.s = s; g.job.f = f; g.job.c = c; g.job.n_threads = n_threads;
+    // reciprocals of every total a block can reach (as prepare_generic of redux_capi.cu sizes them)
+    const uint64_t fmax = ((uint64_t)1 << f) - 1, syms = max_bytes * 8 / s + 1;
+    const uint64_t top = fmax < total + syms ? fmax : total + syms;
+    g.magic.resize((size_t)(top - total + 2));
+    for (size_t i = 0; i < g.magic.size(); ++i) g.magic[i] = make_magic65(total + i);
+    g.job.magic = g.magic.data(); g.job.magic_len = (uint32_t)g.magic.size();
 }
 
 template <typename K>
@@ -261,7 +269,9 @@ extern "C" int emu_encode_generic(uint32_t s, uint32_t f, uint32_t c, const uint
                                   uint8_t *slots, uint64_t slot_stride, uint32_t *sizes, int32_t *status)
 {
     GenericSetup g;
-    generic_setup(g, s, f, c, freq, n_threads);
+    uint64_t max_bytes = 0;
+    for (uint64_t i = 0; i < n_blocks; ++i) max_bytes = std::max<uint64_t>(max_bytes, in_off[i + 1] - in_off[i]);
+    generic_setup(g, s, f, c, freq, n_threads, max_bytes);
     g.job.in = in; g.job.in_off = in_off; g.job.n_blocks = n_blocks;
     g.job.slots = slots; g.job.slot_stride = slot_stride; g.job.sizes = sizes; g.job.status = status;
     run_generic(encode_generic_kernel, g.job);
@@ -274,7 +284,9 @@ extern "C" int emu_decode_generic(uint32_t s, uint32_t f, uint32_t c, const uint
                                   int32_t *status)
 {
     GenericSetup g;
-    generic_setup(g, s, f, c, freq, n_threads);
+    uint64_t max_bytes = 0;
+    for (uint64_t i = 0; i < n_blocks; ++i) max_bytes = std::max<uint64_t>(max_bytes, raw_off[i + 1] - raw_off[i]);
+    generic_setup(g, s, f, c, freq, n_threads, max_bytes);
     g.job.in = comp; g.job.in_off = comp_off; g.job.n_blocks = n_blocks;
     g.job.raw = raw; g.job.raw_off = raw_off; g.job.raw_len = raw_len; g.job.consumed = consumed; g.job.status = status;
     run_generic(decode_generic_kernel, g.job);
