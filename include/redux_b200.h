@@ -87,9 +87,12 @@ int redux_process_init(void);
 /* ---- host memory for the host-buffer API.  redux_encode_batch / redux_decode_batch copy straight from / to the
  * caller's pointers (the reference streams through &mut io::Read / io::Write, src/lib.rs:102-109; a binding lands
  * that in a byte buffer).  Page-locked buffers make those copies asynchronous so the chunk
- * pipeline overlaps them with the kernels; pageable buffers work, at roughly host-memcpy speed (bench.py reports
- * both).  redux_host_alloc returns page-locked memory usable with every device; redux_host_register page-locks
- * an existing allocation (e.g. a long-lived Vec<u8>) in place -- pinning costs ~0.1 ms per MiB, so do it once. */
+ * pipeline overlaps them with the kernels.  Pageable buffers (a plain Vec<u8>) work too: the library stages them
+ * itself through a small ring of pinned slots filled / emptied by a few host copy threads (redux_ctx_set_staging),
+ * so the pipeline stays asynchronous at the speed the host can memcpy (bench.py reports pinned, registered, staged
+ * and driver-staged numbers).  redux_host_alloc returns page-locked memory usable with every device;
+ * redux_host_register page-locks an existing allocation (e.g. a long-lived Vec<u8>) in place -- pinning costs
+ * ~0.1 ms per MiB, so do it once. */
 int redux_host_alloc(size_t bytes, void **out);
 int redux_host_free(void *p);
 int redux_host_register(void *p, size_t bytes);
@@ -103,6 +106,13 @@ int  redux_ctx_device_count(const redux_ctx_t *ctx);
 const char *redux_ctx_last_error(const redux_ctx_t *ctx);
 /* REDUX_SCHED_*; default AUTO. */
 int  redux_ctx_set_schedule(redux_ctx_t *ctx, int sched);
+/* How redux_encode_batch / redux_decode_batch treat caller buffers that are neither page-locked nor registered.
+ * enable != 0 (default): transfers of at least min_bytes go through `slots` pinned slots of piece_bytes each per
+ * device and direction, copied by `threads` host threads (0 = chosen from the core count) created on first use and
+ * joined by redux_ctx_destroy; enable == 0: such pointers are handed to cudaMemcpyAsync as they are (the driver's own
+ * synchronous staging).  A zero size / count keeps the current value.  Defaults: 8 MiB, 8 MiB, 4 slots.  Results
+ * are identical either way.  Call it between batch calls, not during one. */
+int  redux_ctx_set_staging(redux_ctx_t *ctx, int enable, size_t min_bytes, size_t piece_bytes, int slots, int threads);
 /* Number of kernels this context has launched so far (for bench.py's gpu_launches). */
 uint64_t redux_ctx_kernel_launches(const redux_ctx_t *ctx);
 

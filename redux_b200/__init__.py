@@ -112,6 +112,7 @@ def lib():
     L.redux_ctx_last_error.argtypes = [vp]
     L.redux_ctx_last_error.restype = C.c_char_p
     L.redux_ctx_set_schedule.argtypes = [vp, i32]
+    L.redux_ctx_set_staging.argtypes = [vp, i32, C.c_size_t, C.c_size_t, i32, i32]
     L.redux_ctx_kernel_launches.argtypes = [vp]
     L.redux_ctx_kernel_launches.restype = u64
     L.redux_ctx_synchronize.argtypes = [vp, i32, vp]
@@ -349,6 +350,11 @@ class Context:
 
     def set_schedule(self, sched):
         _raise(lib().redux_ctx_set_schedule(self._h, sched), self)
+
+    def set_staging(self, enable=True, min_bytes=0, piece_bytes=0, slots=0, threads=0):
+        """How pageable (not page-locked) caller buffers are moved: through the library's pinned ring and copy
+        threads (default), or handed to the driver as they are.  Zero keeps a value."""
+        _raise(lib().redux_ctx_set_staging(self._h, 1 if enable else 0, min_bytes, piece_bytes, slots, threads), self)
 
     def timing_enable(self, on=True):
         _raise(lib().redux_ctx_timing_enable(self._h, 1 if on else 0), self)

@@ -8,7 +8,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <atomic>
 #include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <cstdio>
 #include <cstdlib>
@@ -76,6 +78,96 @@ struct HostBuf {
 
 constexpr int kPipeStreams = 16;          // one compute stream per chunk in flight (host-buffer API)
 
+// ------------------------------------------------------------------ pageable host memory: library-side staging
+// The crate's callers hold plain Vec<u8>s (src/lib.rs:102-120 streams through io::Read / io::Write;
+// INTEGRATION.md lands that in pageable memory).  cudaMemcpyAsync on pageable memory is staged by the driver through
+// one bounce buffer on the CALLING thread, synchronously: the chunk pipeline of the host-buffer API collapses into
+// copy, compute, copy one after the other (measured 3.4 GB/s end to end against 21.7 GB/s from pinned buffers,
+// profiles/r02_bench_default.json).  When a caller's buffer is neither pinned nor registered the library therefore
+// stages it itself: a few host threads copy piece after piece between the caller's memory and a small ring of
+// pinned slots, and the asynchronous copies run between the ring and the device, so host copies, PCIe transfers in
+// both directions and the kernels overlap as they do from pinned buffers.
+class CopyPool {
+    struct Task { uint8_t *dst; const uint8_t *src; size_t n; int *left; };
+    std::vector<std::thread> workers;
+    std::deque<Task> q;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    bool stop = false;
+
+    void run() {
+        std::unique_lock<std::mutex> l(m);
+        for (;;) {
+            cv_work.wait(l, [&] { return stop || !q.empty(); });
+            if (q.empty()) return;                          // stop requested and nothing left
+            Task t = q.front(); q.pop_front();
+            l.unlock();
+            std::memcpy(t.dst, t.src, t.n);
+            l.lock();
+            if (--*t.left == 0) cv_done.notify_all();
+        }
+    }
+public:
+    explicit CopyPool(int n_workers) { for (int i = 0; i < n_workers; ++i) workers.emplace_back([this] { run(); }); }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> l(m); stop = true; }
+        cv_work.notify_all();
+        for (auto &t : workers) t.join();
+    }
+    // memcpy cut into one slice per thread (the caller copies a slice itself); returns when all of it has landed.
+    // Safe to call from several threads at once.
+    void copy(void *dst_, const void *src_, size_t n) {
+        uint8_t *dst = (uint8_t *)dst_; const uint8_t *src = (const uint8_t *)src_;
+        constexpr size_t kMinSlice = 256 << 10;
+        size_t parts = std::min<size_t>(workers.size() + 1, (n + kMinSlice - 1) / kMinSlice);
+        if (parts <= 1) { std::memcpy(dst, src, n); return; }
+        const size_t per = ((n + parts - 1) / parts + 63) & ~(size_t)63;
+        int left = 0;
+        {
+            std::lock_guard<std::mutex> l(m);
+            for (size_t a = per; a < n; a += per) { q.push_back({dst + a, src + a, std::min(per, n - a), &left}); ++left; }
+        }
+        cv_work.notify_all();
+        std::memcpy(dst, src, std::min(per, n));
+        std::unique_lock<std::mutex> l(m);
+        cv_done.wait(l, [&] { return left == 0; });
+    }
+};
+
+// Ring of pinned slots between the caller's pageable memory and one copy stream; a slot's event says when the
+// asynchronous copy that used it last has finished.
+struct StageRing {
+    uint8_t *buf = nullptr; size_t piece = 0; int n = 0;
+    std::vector<cudaEvent_t> ev;
+    std::vector<char> recorded;
+    cudaError_t ensure(size_t piece_bytes, int slots) {
+        if (buf && piece == piece_bytes && n == slots) return cudaSuccess;
+        release();
+        cudaError_t e = cudaHostAlloc((void **)&buf, piece_bytes * (size_t)slots, cudaHostAllocDefault);
+        if (e != cudaSuccess) { buf = nullptr; return e; }
+        piece = piece_bytes; n = slots;
+        ev.assign((size_t)slots, nullptr); recorded.assign((size_t)slots, 0);
+        for (auto &x : ev) if ((e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    void release() {
+        for (auto x : ev) if (x) cudaEventDestroy(x);
+        ev.clear(); recorded.clear();
+        if (buf) cudaFreeHost(buf);
+        buf = nullptr; piece = 0; n = 0;
+    }
+    uint8_t *slot(int i) const { return buf + (size_t)i * piece; }
+};
+
+// How the host-buffer calls treat pageable memory (redux_ctx_set_staging).
+struct StagingConfig {
+    int enable = 1;                       // 0: hand pageable pointers to cudaMemcpyAsync as they are
+    size_t min_bytes = (size_t)8 << 20;   // smaller transfers are not worth a ring and a feeder thread
+    size_t piece_bytes = (size_t)8 << 20;
+    int slots = 4;
+    int threads = 0;                      // copy threads; 0 = chosen from the host's core count
+};
+
 struct DeviceState {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -97,6 +189,8 @@ struct DeviceState {
     // device, asynchronous to the host all the same.
     cudaEvent_t ws_busy = nullptr;
     bool ws_recorded = false;
+    // pinned rings of the pageable-memory path (pointers: DeviceState is copied into per-thread views)
+    StageRing *ring_up = nullptr, *ring_down = nullptr;
 };
 
 }  // namespace
@@ -111,6 +205,8 @@ struct redux_ctx {
     bool timing = false;                  // bracket every kernel with CUDA events (bench.py)
     const uint32_t *model_freq = nullptr;  // pre-trained start state of the running *_ex call (host pointer)
     std::vector<TimedSpan> spans;
+    StagingConfig staging;
+    CopyPool *pool = nullptr;              // created by the first call that meets pageable memory
 };
 
 namespace {
@@ -728,7 +824,9 @@ extern "C" void redux_ctx_destroy(redux_ctx_t *ctx)
                           &d.st_status, &d.st_aux0, &d.st_aux1, &d.st_roff, &d.corpus, &d.gen_magic, &d.gen_tabs, &d.gen_init, &d.gen_freq, &d.split_hist, &d.split_pairs}) b->release();
         for (auto &m : d.magics) cudaFree(m.ptr);
         if (d.text_lut) cudaFree(d.text_lut);
+        for (StageRing *r : {d.ring_up, d.ring_down}) if (r) { r->release(); delete r; }
     }
+    delete ctx->pool;
     delete ctx;
 }
 
@@ -779,6 +877,23 @@ extern "C" int redux_ctx_set_schedule(redux_ctx_t *ctx, int sched)
     if (!ctx) return REDUX_INVALID_INPUT;
     if (sched == REDUX_SCHED_AUTO || sched == REDUX_SCHED_LANE || sched == REDUX_SCHED_WARP || sched == REDUX_SCHED_SPLIT) { ctx->sched = sched; return REDUX_OK; }
     return fail(ctx, REDUX_INVALID_INPUT, "unknown schedule");
+}
+
+extern "C" int redux_ctx_set_staging(redux_ctx_t *ctx, int enable, size_t min_bytes, size_t piece_bytes, int slots, int threads)
+{
+    if (!ctx) return REDUX_INVALID_INPUT;
+    if (slots < 0 || threads < 0 || slots > 64 || threads > 256) return fail(ctx, REDUX_INVALID_INPUT, "staging: slots / threads out of range");
+    if (piece_bytes && (piece_bytes < 4096 || piece_bytes > ((size_t)1 << 30))) return fail(ctx, REDUX_INVALID_INPUT, "staging: piece_bytes out of range");
+    ctx->staging.enable = enable != 0;
+    if (min_bytes) ctx->staging.min_bytes = min_bytes;
+    if (piece_bytes) ctx->staging.piece_bytes = (piece_bytes + 63) & ~(size_t)63;
+    if (slots) ctx->staging.slots = std::max(2, slots);
+    if (threads && threads != ctx->staging.threads) {
+        ctx->staging.threads = threads;
+        delete ctx->pool;                     // no call is running: the next one recreates it
+        ctx->pool = nullptr;
+    }
+    return REDUX_OK;
 }
 
 extern "C" int redux_ctx_synchronize(redux_ctx_t *ctx, int device, void *stream)
@@ -1071,10 +1186,11 @@ void for_each_device(redux_ctx *ctx, size_t nd, std::vector<int> &rcs, F fn)
     std::vector<std::vector<TimedSpan>> spans(nd);
     for (size_t g = 0; g < nd; ++g) th.emplace_back([&, g] {
         redux_ctx view; view.sched = ctx->sched; view.timing = ctx->timing; view.model_freq = ctx->model_freq;
+        view.staging = ctx->staging; view.pool = ctx->pool;
         view.devs.push_back(ctx->devs[g]);
         rcs[g] = fn(&view, &view.devs[0], g);
         ctx->devs[g] = view.devs[0];          // workspaces may have grown
-        view.devs.clear();
+        view.devs.clear(); view.pool = nullptr;
         errs[g] = view.last_error; launches[g] = view.launches; spans[g] = view.spans;
     });
     for (auto &t : th) t.join();
@@ -1092,6 +1208,114 @@ void drain(DeviceState *d)
     for (int i = 0; i < kPipeStreams; ++i) cudaStreamSynchronize(d->pipe[i]);
     cudaStreamSynchronize(d->copy);
 }
+
+// ---- pageable caller memory (see CopyPool)
+// true when `p` is host memory CUDA does not know (neither cudaHostAlloc'ed nor registered) and the transfer is big
+// enough to be worth staging
+bool needs_staging(const redux_ctx *ctx, const void *p, uint64_t bytes)
+{
+    if (!ctx->staging.enable || !p || bytes < ctx->staging.min_bytes) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// creates the copy threads on first use (called before the per-device workers start)
+void ensure_pool(redux_ctx *ctx)
+{
+    if (ctx->pool) return;
+    int n = ctx->staging.threads;
+    if (n <= 0) {
+        // measured on a 16-core host (profiles/r02_staging.json): 1 thread 6.2, 4: 11.4, 8: 14.1, 12: 16.1 GB/s end to
+        // end (pinned buffers: 19.7); the feeder and the drainer copy too
+        const int hw = (int)std::thread::hardware_concurrency();
+        n = std::max(1, std::min(16, hw * 3 / 4));
+    }
+    ctx->pool = new CopyPool(n);
+}
+
+cudaError_t ensure_ring(const redux_ctx *ctx, StageRing **ring)
+{
+    if (!*ring) *ring = new StageRing();
+    return (*ring)->ensure(ctx->staging.piece_bytes, std::max(2, ctx->staging.slots));
+}
+
+// Host -> device through the ring: blocks the calling (feeder) thread for the host copies only.
+cudaError_t staged_h2d(StageRing *ring, CopyPool *pool, cudaStream_t stream, uint8_t *dst_dev, const uint8_t *src,
+                       uint64_t n, int *next_slot, const std::atomic<bool> *stop)
+{
+    for (uint64_t a = 0; a < n; a += ring->piece) {
+        if (stop && stop->load(std::memory_order_relaxed)) return cudaSuccess;
+        const size_t len = (size_t)std::min<uint64_t>(ring->piece, n - a);
+        const int i = *next_slot;
+        *next_slot = (i + 1) % ring->n;
+        cudaError_t e;
+        if (ring->recorded[i] && (e = cudaEventSynchronize(ring->ev[i])) != cudaSuccess) return e;
+        pool->copy(ring->slot(i), src + a, len);
+        if ((e = cudaMemcpyAsync(dst_dev + a, ring->slot(i), len, cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(ring->ev[i], stream)) != cudaSuccess) return e;
+        ring->recorded[i] = 1;
+    }
+    return cudaSuccess;
+}
+
+// Device -> host through the ring, driven by the drainer thread: push() enqueues the asynchronous copies of one
+// range piece by piece and, when the ring is full, first retires the oldest piece (waits for it, copies it to the
+// caller's memory); flush() retires everything.
+struct DownStager {
+    StageRing *ring; CopyPool *pool; cudaStream_t stream;
+    struct Pending { int slot; uint8_t *dst; size_t n; };
+    std::deque<Pending> fifo;
+    int next = 0;
+    cudaError_t retire_one() {
+        const Pending p = fifo.front(); fifo.pop_front();
+        cudaError_t e = cudaEventSynchronize(ring->ev[p.slot]);
+        if (e != cudaSuccess) return e;
+        pool->copy(p.dst, ring->slot(p.slot), p.n);
+        return cudaSuccess;
+    }
+    cudaError_t push(uint8_t *dst_host, const uint8_t *src_dev, uint64_t n) {
+        for (uint64_t a = 0; a < n; a += ring->piece) {
+            cudaError_t e;
+            if ((int)fifo.size() == ring->n && (e = retire_one()) != cudaSuccess) return e;
+            const size_t len = (size_t)std::min<uint64_t>(ring->piece, n - a);
+            const int i = next; next = (next + 1) % ring->n;
+            if ((e = cudaMemcpyAsync(ring->slot(i), src_dev + a, len, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(ring->ev[i], stream)) != cudaSuccess) return e;
+            ring->recorded[i] = 1;
+            fifo.push_back({i, dst_host + a, len});
+        }
+        return cudaSuccess;
+    }
+    // retires finished pieces while `gate` (an event the caller is about to wait for) is still pending
+    cudaError_t retire_while_pending(cudaEvent_t gate) {
+        while (!fifo.empty() && cudaEventQuery(gate) == cudaErrorNotReady) {
+            cudaError_t e = retire_one();
+            if (e != cudaSuccess) return e;
+        }
+        (void)cudaGetLastError();                           // cudaErrorNotReady is not an error
+        return cudaSuccess;
+    }
+    cudaError_t flush() {
+        while (!fifo.empty()) { cudaError_t e = retire_one(); if (e != cudaSuccess) return e; }
+        return cudaSuccess;
+    }
+};
+
+// Hand-off between the thread that enqueues the chunks (and feeds the staged input) and the thread that drains
+// their results: chunk k may be waited for once `enqueued > k`.
+struct ChunkProgress {
+    std::mutex m; std::condition_variable cv;
+    size_t enqueued = 0; bool done = false;
+    std::atomic<bool> stop{false};                          // the drainer failed: stop feeding
+    void advance() { { std::lock_guard<std::mutex> l(m); ++enqueued; } cv.notify_all(); }
+    void finish() { { std::lock_guard<std::mutex> l(m); done = true; } cv.notify_all(); }
+    bool wait_for(size_t k) {                               // false: the feeder ended before chunk k
+        std::unique_lock<std::mutex> l(m);
+        cv.wait(l, [&] { return enqueued > k || done; });
+        return enqueued > k;
+    }
+};
 
 // Cross-shard hand-off of redux_encode_batch on several devices.  The streams of the whole batch lie back to
 // back in the caller's buffer, so shard g's bytes start where the shards below it end: every worker publishes
@@ -1186,6 +1410,12 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     if ((rc = prepare_generic(ctx, d, d->h2d, p, sh.count, &pl))) return rc;
     EventSet evs;                       // [0, nc): chunk done; [nc, 2nc): chunk input on the device
     CU_TRY(ctx, evs.create(2 * nc));
+    // pageable caller memory goes through the pinned rings (CopyPool); then the enqueue loop below runs on a feeder
+    // thread of its own, because it blocks on host copies while the results of earlier chunks are being drained
+    const bool stage_in = needs_staging(ctx, in, bytes), stage_out = needs_staging(ctx, out, std::min(out_cap, dcap));
+    const bool staged = stage_in || stage_out;
+    if (stage_in) CU_TRY(ctx, ensure_ring(ctx, &d->ring_up));
+    if (stage_out) CU_TRY(ctx, ensure_ring(ctx, &d->ring_down));
     CU_TRY(ctx, cudaMemcpyAsync(d->st_off.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d->h2d));
 
     uint8_t *d_in = (uint8_t *)d->st_in.p, *d_out = (uint8_t *)d->st_out.p;
@@ -1193,34 +1423,48 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     int32_t *d_status = (int32_t *)d->st_status.p;
     uint64_t *h_ooff = (uint64_t *)d->pin_off.p;
     int32_t *h_status = (int32_t *)d->pin_status.p;
-    for (size_t k = 0; k < nc; ++k) {
-        const Shard c = res->chunks[k];
-        cudaStream_t s = d->pipe[k % pipe_streams()];
-        rc = REDUX_OK;
-        cudaError_t e = cudaSuccess;
-        const uint64_t b0 = rel[c.first], b1 = rel[c.first + c.count];
-        if (b1 > b0) e = cudaMemcpyAsync(d_in + b0, in + base + b0, b1 - b0, cudaMemcpyHostToDevice, d->h2d);
-        if (e == cudaSuccess) e = cudaEventRecord(evs.ev[nc + k], d->h2d);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[nc + k], 0);
-        if (e == cudaSuccess)
-            rc = encode_launch(ctx, d->device, s, pl, magic, d_in, d_off + c.first, c.count,
-                               d_out + res->chunk_base[k], chunk_cap[k], d_ooff + c.first + k,
-                               d_status + c.first, (uint8_t *)d->slots.p + c.first * pl.slot_stride,
-                               (uint32_t *)d->sizes.p + c.first, (int32_t *)d->flag.p + k);
-        if (e == cudaSuccess && rc == REDUX_OK)
-            e = cudaMemcpyAsync(h_ooff + c.first + k, d_ooff + c.first + k, (c.count + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && rc == REDUX_OK)
-            e = cudaMemcpyAsync(h_status + c.first, d_status + c.first, c.count * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && rc == REDUX_OK) e = cudaEventRecord(evs.ev[k], s);
-        if (e != cudaSuccess || rc != REDUX_OK) {
-            drain(d);
-            if (rc != REDUX_OK) return rc;
-            (void)cudaGetLastError();
-            return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline enqueue", e);
+    ChunkProgress prog;
+    // While the feeder runs it is the only thread that touches ctx (error text, launch counter, timing spans).
+    auto enqueue_all = [&]() -> int {
+        int up_slot = 0;
+        for (size_t k = 0; k < nc && !prog.stop.load(std::memory_order_relaxed); ++k) {
+            const Shard c = res->chunks[k];
+            cudaStream_t s = d->pipe[k % pipe_streams()];
+            int rc2 = REDUX_OK;
+            cudaError_t e = cudaSuccess;
+            const uint64_t b0 = rel[c.first], b1 = rel[c.first + c.count];
+            if (b1 > b0) e = stage_in ? staged_h2d(d->ring_up, ctx->pool, d->h2d, d_in + b0, in + base + b0, b1 - b0, &up_slot, &prog.stop)
+                                      : cudaMemcpyAsync(d_in + b0, in + base + b0, b1 - b0, cudaMemcpyHostToDevice, d->h2d);
+            if (e == cudaSuccess) e = cudaEventRecord(evs.ev[nc + k], d->h2d);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[nc + k], 0);
+            if (e == cudaSuccess)
+                rc2 = encode_launch(ctx, d->device, s, pl, magic, d_in, d_off + c.first, c.count,
+                                    d_out + res->chunk_base[k], chunk_cap[k], d_ooff + c.first + k,
+                                    d_status + c.first, (uint8_t *)d->slots.p + c.first * pl.slot_stride,
+                                    (uint32_t *)d->sizes.p + c.first, (int32_t *)d->flag.p + k);
+            if (e == cudaSuccess && rc2 == REDUX_OK)
+                e = cudaMemcpyAsync(h_ooff + c.first + k, d_ooff + c.first + k, (c.count + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && rc2 == REDUX_OK)
+                e = cudaMemcpyAsync(h_status + c.first, d_status + c.first, c.count * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && rc2 == REDUX_OK) e = cudaEventRecord(evs.ev[k], s);
+            if (rc2 != REDUX_OK) return rc2;
+            if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline enqueue", e); }
+            prog.advance();
         }
+        return REDUX_OK;
+    };
+    int feeder_rc = REDUX_OK;
+    std::thread feeder;
+    if (staged) {
+        feeder = std::thread([&] { DeviceGuard fg(d->device); feeder_rc = enqueue_all(); prog.finish(); });
+    } else {
+        feeder_rc = enqueue_all();
+        prog.finish();
+        if (feeder_rc != REDUX_OK) { drain(d); return feeder_rc; }
+        tr.mark("encode: all chunks enqueued");
     }
-    tr.mark("encode: all chunks enqueued");
     // in order: offsets of chunk k become shard-local offsets; its bytes go out while later chunks run
+    DownStager down{d->ring_down, ctx->pool, d->copy, {}, 0};
     uint64_t pos = 0;
     // copies the prefix of chunk k that fits the caller's buffer to out + at
     auto place = [&](size_t k, uint64_t at) -> cudaError_t {
@@ -1228,36 +1472,53 @@ int encode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
         if (at >= out_cap) return cudaSuccess;
         if (at + nbytes > out_cap) nbytes = out_cap - at;
         if (!nbytes) return cudaSuccess;
+        if (stage_out) return down.push(out + at, d_out + res->chunk_base[k], nbytes);
         return cudaMemcpyAsync(out + at, d_out + res->chunk_base[k], nbytes, cudaMemcpyDeviceToHost, d->copy);
     };
-    for (size_t k = 0; k < nc; ++k) {
+    cudaError_t derr = cudaSuccess;                         // first error of this (draining) thread
+    const char *dwhat = "encode pipeline";
+    bool other_failed = false;
+    size_t k_done = 0;
+    for (; k_done < nc; ++k_done) {
+        const size_t k = k_done;
         const Shard c = res->chunks[k];
-        cudaError_t e = cudaEventSynchronize(evs.ev[k]);
-        if (e != cudaSuccess) { drain(d); (void)cudaGetLastError(); return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline", e); }
+        if (!prog.wait_for(k)) break;                       // the feeder gave up: its code is the call's
+        if (stage_out && (derr = down.retire_while_pending(evs.ev[k])) != cudaSuccess) break;
+        if ((derr = cudaEventSynchronize(evs.ev[k])) != cudaSuccess) break;
         tr.mark("encode: chunk done", (long)k);
         const uint64_t *lo = h_ooff + c.first + k;
         for (uint64_t i = 0; i <= c.count; ++i) res->local_off[c.first + i] = pos + lo[i];
         std::memcpy(status + c.first, h_status + c.first, c.count * sizeof(int32_t));
         res->chunk_total[k] = lo[c.count];
-        if (streaming && (e = place(k, pos)) != cudaSuccess) {
-            drain(d); (void)cudaGetLastError();
-            return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline D2H", e);
-        }
+        if (streaming && (derr = place(k, pos)) != cudaSuccess) { dwhat = "encode pipeline D2H"; break; }
         pos += lo[c.count];
     }
-    res->total = pos;
-    if (sync) sync->publish(g_index, pos);
-    if (!streaming) {
-        uint64_t at = 0;
-        if (!sync->base_of(g_index, &at)) { drain(d); return REDUX_OK; }     // another shard failed: its code is the call's
-        tr.mark("encode: base known");
-        for (size_t k = 0; k < nc; ++k) {
-            cudaError_t e = place(k, at);
-            if (e != cudaSuccess) { drain(d); (void)cudaGetLastError(); return fail(ctx, REDUX_CUDA_ERROR, "encode pipeline D2H", e); }
-            at += res->chunk_total[k];
+    if (k_done == nc) {
+        res->total = pos;
+        if (sync) sync->publish(g_index, pos);
+        if (!streaming) {
+            uint64_t at = 0;
+            if (!sync->base_of(g_index, &at)) other_failed = true;      // another shard failed: its code is the call's
+            else {
+                tr.mark("encode: base known");
+                for (size_t k = 0; k < nc && derr == cudaSuccess; ++k) {
+                    if ((derr = place(k, at)) != cudaSuccess) dwhat = "encode pipeline D2H";
+                    at += res->chunk_total[k];
+                }
+            }
+        }
+        if (derr == cudaSuccess && !other_failed) {
+            derr = stage_out ? down.flush() : cudaStreamSynchronize(d->copy);
+            if (derr != cudaSuccess) dwhat = "encode pipeline D2H";
         }
     }
-    CU_TRY(ctx, cudaStreamSynchronize(d->copy));
+    if (feeder.joinable()) {
+        if (derr != cudaSuccess || other_failed) prog.stop.store(true);
+        feeder.join();
+    }
+    if (feeder_rc != REDUX_OK) { drain(d); return feeder_rc; }
+    if (other_failed) { drain(d); return REDUX_OK; }
+    if (derr != cudaSuccess) { drain(d); (void)cudaGetLastError(); return fail(ctx, REDUX_CUDA_ERROR, dwhat, derr); }
     tr.mark("encode: last D2H done");
     return REDUX_OK;
 }
@@ -1277,6 +1538,7 @@ extern "C" int redux_encode_batch(redux_ctx_t *ctx, int model_kind, const redux_
     out_offsets[0] = 0;
     if (n_blocks == 0) return REDUX_OK;
 
+    if (needs_staging(ctx, in, in_offsets[n_blocks] - in_offsets[0]) || needs_staging(ctx, out, out_capacity)) ensure_pool(ctx);
     const size_t nd = std::min<uint64_t>(ctx->devs.size(), n_blocks);
     std::vector<Shard> shards = make_shards(n_blocks, nd);
     std::vector<EncShardOut> res(nd);
@@ -1348,8 +1610,13 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     const void *magic = nullptr;
     if ((rc = get_magic(ctx, d, d->pipe[0], pl, &magic))) return rc;
     if ((rc = prepare_generic(ctx, d, d->pipe[0], p, sh.count, &pl))) return rc;
-    EventSet evs;                       // chunk input on the device
-    CU_TRY(ctx, evs.create(nc));
+    EventSet evs;                       // [0, nc): chunk input on the device; [nc, 2nc): chunk decoded
+    CU_TRY(ctx, evs.create(2 * nc));
+    // pageable caller memory: see encode_shard
+    const bool stage_in = needs_staging(ctx, comp, cbytes), stage_out = needs_staging(ctx, raw, rbytes);
+    const bool staged = stage_in || stage_out;
+    if (stage_in) CU_TRY(ctx, ensure_ring(ctx, &d->ring_up));
+    if (stage_out) CU_TRY(ctx, ensure_ring(ctx, &d->ring_down));
     CU_TRY(ctx, cudaMemcpyAsync(d->st_off.p, rel.data(), rel.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, d->h2d));
     uint8_t *d_comp = (uint8_t *)d->st_in.p, *d_raw = (uint8_t *)d->st_out.p;
     uint64_t *d_coff = (uint64_t *)d->st_off.p, *d_roff = d_coff + sh.count + 1;
@@ -1357,35 +1624,67 @@ int decode_shard(redux_ctx *ctx, DeviceState *d, int kind, const redux_params_t 
     int32_t *d_status = (int32_t *)d->st_status.p;
     uint64_t *h_len = (uint64_t *)d->pin_aux0.p, *h_cons = (uint64_t *)d->pin_aux1.p;
     int32_t *h_status = (int32_t *)d->pin_status.p;
-    for (size_t k = 0; k < nc; ++k) {
-        const Shard c = chunks[k];
-        cudaStream_t s = d->pipe[k % pipe_streams()];
-        rc = REDUX_OK;
-        cudaError_t e = cudaSuccess;
-        const uint64_t c0 = crel[c.first], c1 = crel[c.first + c.count];
-        const uint64_t r0 = rrel[c.first], r1 = rrel[c.first + c.count];
-        if (c1 > c0) e = cudaMemcpyAsync(d_comp + c0, comp + cbase + c0, c1 - c0, cudaMemcpyHostToDevice, d->h2d);
-        if (e == cudaSuccess) e = cudaEventRecord(evs.ev[k], d->h2d);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[k], 0);
-        if (e == cudaSuccess)
-            rc = decode_launch(ctx, d->device, s, pl, magic, d_comp, d_coff + c.first, c.count, d_raw,
-                               d_roff + c.first, d_len + c.first, d_cons + c.first, d_status + c.first);
-        // the whole slot range of the chunk goes back; bytes beyond raw_lens[i] inside a slot are unspecified
-        if (e == cudaSuccess && rc == REDUX_OK && r1 > r0)
-            e = cudaMemcpyAsync(raw + rbase + r0, d_raw + r0, r1 - r0, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && rc == REDUX_OK)
-            e = cudaMemcpyAsync(h_len + c.first, d_len + c.first, c.count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && rc == REDUX_OK)
-            e = cudaMemcpyAsync(h_cons + c.first, d_cons + c.first, c.count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess && rc == REDUX_OK)
-            e = cudaMemcpyAsync(h_status + c.first, d_status + c.first, c.count * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess || rc != REDUX_OK) {
-            drain(d);
-            if (rc != REDUX_OK) return rc;
-            (void)cudaGetLastError();
-            return fail(ctx, REDUX_CUDA_ERROR, "decode pipeline enqueue", e);
+    ChunkProgress prog;
+    auto enqueue_all = [&]() -> int {
+        int up_slot = 0;
+        for (size_t k = 0; k < nc && !prog.stop.load(std::memory_order_relaxed); ++k) {
+            const Shard c = chunks[k];
+            cudaStream_t s = d->pipe[k % pipe_streams()];
+            int rc2 = REDUX_OK;
+            cudaError_t e = cudaSuccess;
+            const uint64_t c0 = crel[c.first], c1 = crel[c.first + c.count];
+            const uint64_t r0 = rrel[c.first], r1 = rrel[c.first + c.count];
+            if (c1 > c0) e = stage_in ? staged_h2d(d->ring_up, ctx->pool, d->h2d, d_comp + c0, comp + cbase + c0, c1 - c0, &up_slot, &prog.stop)
+                                      : cudaMemcpyAsync(d_comp + c0, comp + cbase + c0, c1 - c0, cudaMemcpyHostToDevice, d->h2d);
+            if (e == cudaSuccess) e = cudaEventRecord(evs.ev[k], d->h2d);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(s, evs.ev[k], 0);
+            if (e == cudaSuccess)
+                rc2 = decode_launch(ctx, d->device, s, pl, magic, d_comp, d_coff + c.first, c.count, d_raw,
+                                    d_roff + c.first, d_len + c.first, d_cons + c.first, d_status + c.first);
+            // the whole slot range of the chunk goes back; bytes beyond raw_lens[i] inside a slot are unspecified
+            // (into pageable memory: by the drainer below, through the ring)
+            if (e == cudaSuccess && rc2 == REDUX_OK && stage_out) e = cudaEventRecord(evs.ev[nc + k], s);
+            if (e == cudaSuccess && rc2 == REDUX_OK && !stage_out && r1 > r0)
+                e = cudaMemcpyAsync(raw + rbase + r0, d_raw + r0, r1 - r0, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && rc2 == REDUX_OK)
+                e = cudaMemcpyAsync(h_len + c.first, d_len + c.first, c.count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && rc2 == REDUX_OK)
+                e = cudaMemcpyAsync(h_cons + c.first, d_cons + c.first, c.count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess && rc2 == REDUX_OK)
+                e = cudaMemcpyAsync(h_status + c.first, d_status + c.first, c.count * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+            if (rc2 != REDUX_OK) return rc2;
+            if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, REDUX_CUDA_ERROR, "decode pipeline enqueue", e); }
+            prog.advance();
         }
+        return REDUX_OK;
+    };
+    int feeder_rc = REDUX_OK;
+    std::thread feeder;
+    if (staged) {
+        feeder = std::thread([&] { DeviceGuard fg(d->device); feeder_rc = enqueue_all(); prog.finish(); });
+    } else {
+        feeder_rc = enqueue_all();
+        prog.finish();
     }
+    cudaError_t derr = cudaSuccess;
+    if (stage_out) {
+        // chunk k's decoded slots leave on the copy stream once its kernel is done, piece by piece through the ring
+        DownStager down{d->ring_down, ctx->pool, d->copy, {}, 0};
+        for (size_t k = 0; k < nc && derr == cudaSuccess; ++k) {
+            if (!prog.wait_for(k)) break;
+            const Shard c = chunks[k];
+            const uint64_t r0 = rrel[c.first], r1 = rrel[c.first + c.count];
+            if ((derr = cudaStreamWaitEvent(d->copy, evs.ev[nc + k], 0)) != cudaSuccess) break;
+            if (r1 > r0) derr = down.push(raw + rbase + r0, d_raw + r0, r1 - r0);
+        }
+        if (derr == cudaSuccess) derr = down.flush();
+    }
+    if (feeder.joinable()) {
+        if (derr != cudaSuccess) prog.stop.store(true);
+        feeder.join();
+    }
+    if (feeder_rc != REDUX_OK) { drain(d); return feeder_rc; }
+    if (derr != cudaSuccess) { drain(d); (void)cudaGetLastError(); return fail(ctx, REDUX_CUDA_ERROR, "decode pipeline D2H", derr); }
     tr.mark("decode: all chunks enqueued");
     for (int i = 0; i < kPipeStreams; ++i) { CU_TRY(ctx, cudaStreamSynchronize(d->pipe[i])); tr.mark("decode: stream drained", i); }
     std::memcpy(raw_lens + sh.first, h_len, sh.count * sizeof(uint64_t));
@@ -1409,6 +1708,8 @@ extern "C" int redux_decode_batch(redux_ctx_t *ctx, int model_kind, const redux_
     if (n_blocks == 0) return REDUX_OK;
     if (!comp_offsets || !raw_offsets || !raw_lens || !consumed || !status)
         return fail(ctx, REDUX_INVALID_INPUT, "NULL buffer");
+    if (needs_staging(ctx, comp, comp_offsets[n_blocks] - comp_offsets[0]) ||
+        needs_staging(ctx, raw, raw_offsets[n_blocks] - raw_offsets[0])) ensure_pool(ctx);
     const size_t nd = std::min<uint64_t>(ctx->devs.size(), n_blocks);
     std::vector<Shard> shards = make_shards(n_blocks, nd);
     std::vector<int> rcs(nd, REDUX_OK);

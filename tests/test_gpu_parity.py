@@ -479,6 +479,77 @@ def test_pinned_host_buffers_and_registered_buffers():
         hb.close(); out.close()
 
 
+def test_pageable_buffers_staged_by_the_library():
+    """Pageable caller memory goes through the library's pinned ring and copy threads (redux_ctx_set_staging): same
+    bytes, offsets, counts and statuses as the driver-staged path and the oracle -- with pieces small enough that the
+    ring wraps many times inside every chunk, for pageable input, output, or both, several chunks per call."""
+    rng = np.random.default_rng(11)
+    n = 6000                                                  # > 3 chunks of whole CTAs
+    lens = rng.integers(0, 700, n)
+    blocks = [rb.generate_blocks_host(i, 1, int(L), SEED).tobytes() if L else b"" for i, L in enumerate(lens)]
+    data, off = concat(blocks)
+    for params in ((8, 14, 16), (8, 30, 32)):
+        model = rb.AdaptiveTreeModel(rb.Parameters(*params))
+        with rb.Context([0]) as c:
+            c.set_staging(False)
+            ref, ref_off, ref_st = c.encode_batch(data, off, model)
+            for i in (0, 1, 2, 999, n - 1):
+                assert ref[int(ref_off[i]):int(ref_off[i + 1])].tobytes() == o.compress(blocks[i], o.TREE, params)[1]
+            raw_off = off.copy()
+            pin_in = rb.HostBuffer(data.size); pin_in.array[:] = data
+            pin_out = rb.HostBuffer(ref.size + 64)
+            pin_back = rb.HostBuffer(data.size)
+            c.set_staging(True, min_bytes=1, piece_bytes=4096 * 3, slots=3, threads=3)
+            for src, dst in ((data, None), (pin_in.array, None), (data, pin_out.array)):
+                comp, coff, st = c.encode_batch(src, off, model, out=dst)
+                assert (coff == ref_off).all() and (st == ref_st).all()
+                assert comp[:int(coff[-1])].tobytes() == ref.tobytes()
+            # decode: a truncated and a garbage stream among the good ones keep their statuses and counts
+            streams = [ref[int(ref_off[i]):int(ref_off[i + 1])].tobytes() for i in range(n)]
+            streams[5] = streams[5][:-3]
+            streams[7] = bytes(rng.integers(0, 256, 400, dtype=np.uint8))
+            bad, bad_off = concat(streams)
+            c.set_staging(False)
+            want = c.decode_batch(bad, bad_off, raw_off, model, check=False)
+            assert want[3][5] != 0 and (np.delete(want[3], [5, 7]) == 0).all()
+            c.set_staging(True, min_bytes=1, piece_bytes=4096 * 3, slots=3, threads=3)
+            pin_comp = rb.HostBuffer(bad.size); pin_comp.array[:] = bad
+            for src, dst in ((bad, None), (pin_comp.array, None), (bad, pin_back.array)):
+                got = c.decode_batch(src, bad_off, raw_off, model, raw=dst, check=False)
+                for a, b in zip(got[1:], want[1:]):
+                    assert (a == b).all()
+                for i in range(n):
+                    lo = int(raw_off[i])
+                    assert got[0][lo:lo + int(got[1][i])].tobytes() == want[0][lo:lo + int(want[1][i])].tobytes(), i
+                    if i not in (5, 7):
+                        assert got[0][lo:lo + int(got[1][i])].tobytes() == blocks[i]
+            pin_comp.close()
+            # a short capacity is reported the same way
+            small = np.zeros(ref.size // 2, dtype=np.uint8)
+            with pytest.raises(rb.OutCapacity):
+                c.encode_batch(data, off, model, out=small)
+            pin_in.close(); pin_out.close(); pin_back.close()
+
+
+def test_pageable_staging_multi_megabyte_default_pieces():
+    """Default staging parameters on a batch big enough to engage them (>= 8 MiB each way): round trip + oracle sample."""
+    n, L = 4096, 8192                                         # 32 MiB
+    raw = rb.generate_blocks_host(0, n, L, SEED)
+    off = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+    model = rb.AdaptiveTreeModel(rb.Parameters(8, 14, 16))
+    with rb.Context([0]) as c:
+        comp, coff, st = c.encode_batch(raw, off, model)
+        assert (st == 0).all()
+        for i in (0, 1, 2, 3, 2047, n - 1):
+            assert comp[int(coff[i]):int(coff[i + 1])].tobytes() == o.compress(raw[i * L:(i + 1) * L].tobytes(), o.TREE, (8, 14, 16))[1]
+        c.set_staging(False)
+        comp2, coff2, _ = c.encode_batch(raw, off, model)
+        assert comp2.tobytes() == comp.tobytes() and (coff2 == coff).all()
+        c.set_staging(True)
+        back, rl, cons, st = c.decode_batch(comp, coff, off, model)
+        assert (st == 0).all() and (rl == L).all() and back.tobytes() == raw.tobytes()
+
+
 def test_device_entry_points_take_a_trained_model():
     """redux_encode_batch_device_ex / redux_decode_batch_device_ex: a model trained before the call, data resident in
     HBM; bytes equal the oracle's compress() from the same trained model."""
