@@ -61,6 +61,36 @@ __device__ __forceinline__ uint32_t top_bits(uint32_t x, uint32_t n) { return __
 template <bool C32>
 __device__ __forceinline__ uint32_t common_prefix(uint32_t x) { return C32 ? (uint32_t)clz32(x) : clz_nz(x); }
 
+__device__ __forceinline__ uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+// Keeps the descent's position in ONE register chain: without it the compiler re-associates the position into
+// two induction chains, one scaled for the table addresses and one for the symbol (two more instructions a round).
+__device__ __forceinline__ void pin_chain(uint32_t &x) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+r"(x));
+#else
+    (void)x;
+#endif
+}
+
+// Shift counts of one symbol's renormalisation (src/codec.rs:62-89) from the left-aligned l2 = low', nh2 = ~high':
+// n1 = E1/E2 shifts = length of the common prefix of low' and high', n = n1 + the E3 shifts.  After the common
+// prefix low' has a 0 and high' a 1; the E3 shifts are the run of positions after that one where low' has 1 and
+// high' has 0, i.e. the run of ones of d = l2 & nh2 that starts at position n1 + 1 (d is zero up to position n1).
+// Shifted up by one that run continues the common prefix seamlessly: (equal bits) | (d << 1) has exactly n leading
+// ones -- position n1 + k is inside or right behind the run, where the bits differ and d << 1 has its first zero.
+// So n needs ONE count-leading-zeros on the chain (round 1 counted n1, shifted by it and counted again: two FLOs
+// of 18 cycles each in series on every symbol of every stream); n1 is counted beside it, off the low/high chain.
+// The operand of the second count can only be zero when low' == high' in all 32 bits (C32).
+template <bool C32>
+__device__ __forceinline__ void renorm_counts(uint32_t l2, uint32_t nh2, uint32_t &n1, uint32_t &n)
+{
+    const uint32_t differ = ~(l2 ^ nh2);                           // low' ^ high'
+    n1 = common_prefix<C32>(differ);
+    n = common_prefix<C32>(differ & ~((l2 & nh2) << 1));
+}
+
 // ------------------------------------------------------------------ Fenwick table, v2 access paths
 // Same lane-interleaved storage as LaneTable<TW>.  FULL: node i holds the reference's tree[i]
 // (lowbit(i) + increments); otherwise increments only (u16 entries that must survive 65,536 updates).
@@ -92,6 +122,38 @@ struct LaneTable2 : LaneTable<TW> {
 #pragma unroll 8
             for (int i = 0; i < kWords; ++i) w[i * 32] = (uint32_t)(i & -i);
         }
+    }
+
+    // Byte-addressed access for the decoder's descent.  A position is the shared-window byte address of a node of
+    // this lane's column (host emulation: the byte offset from the column's start), so a table load is
+    // [position + constant] with nothing to add per access -- the descent's position chain carries the address
+    // itself.
+    static constexpr int kNodeBytes = 32 * (int)sizeof(TW);               // table index (i << 5) in bytes: i * kNodeBytes
+    __device__ __forceinline__ uint32_t pos0() const {
+#if defined(__CUDA_ARCH__)
+        return (uint32_t)__cvta_generic_to_shared(t);
+#else
+        return 0u;
+#endif
+    }
+    __device__ __forceinline__ uint32_t ld_at(uint32_t a) const {
+#if defined(__CUDA_ARCH__)
+        uint32_t v;                                           // a 32-bit destination of a 16-bit load is zero-extended
+        if (sizeof(TW) == 2) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+        else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+        return v;
+#else
+        return *reinterpret_cast<const TW *>(reinterpret_cast<const uint8_t *>(t) + a);
+#endif
+    }
+    __device__ __forceinline__ void st_at(uint32_t a, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+        // a 32-bit source of a 16-bit store is truncated: no conversion instruction
+        if (sizeof(TW) == 2) asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+        else asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+#else
+        *reinterpret_cast<TW *>(reinterpret_cast<uint8_t *>(t) + a) = (TW)v;
+#endif
     }
 
     // (cum(s), cum(s+1)) of adaptive_tree.rs:63-80 and, when UPDATE, update(s+1) of :83-92, sharing the
@@ -353,9 +415,9 @@ __device__ __forceinline__ uint32_t encode_step_al(uint32_t &L, uint32_t &H, uin
     // `one` == 1 << sh, handed in as an opaque value so that quotient * one + L stays a single IMAD
     const uint32_t nh2 = ~((uint32_t)C::divc(nh, g, count) * one + (L - 1u));   // ~high' (:59)
     const uint32_t l2 = (uint32_t)C::divc(nl, g, count) * one + L;              // low'   (:60)
-    const uint32_t n1 = common_prefix<C32>(~(l2 ^ nh2));           // E1/E2 shifts (:63-74)
-    const uint32_t k = clz_nz(~shl_c((l2 & nh2) << 1, n1));        // E3 shifts (:75-83); bit 0 of the operand is set
-    const uint32_t n = n1 + k;                                     // <= c
+    uint32_t n1, n;                                                // E1/E2 shifts (:63-74), all shifts (<= c)
+    renorm_counts<C32>(l2, nh2, n1, n);
+    const uint32_t k = n - n1;                                     // E3 shifts (:75-83)
     pend = sink.put_code(top_bits(l2, n1), n1, pend, k);
     L = shl_c(l2, n) & 0x7FFFFFFFu;                                // :87-88 after the E3 subtraction
     H = ~shl_c(nh2, n) | 0x80000000u;                              // high refills with ones
@@ -664,6 +726,63 @@ struct LaneDecoderAl {
         P plo = 0, phi = 0;
         uint32_t I = 0;                                       // i * 32: the descent's position, in table entries
         bool is_eof;                                          // value >= cum(256) = count - freq(EOF): the EOF symbol
+#ifndef RDX_DEC_PREDICATED
+        if (CLS == kNarrow) {
+            // 4-ary descent in the RESIDUAL domain, without a single predicate.  R = X - (largest boundary known to
+            // be <= X) and N = X - (smallest boundary known to be > X, two's complement: negative).  A round forms the
+            // residuals of its three boundaries cum(i+h) <= cum(i+m) <= cum(i+m+h) (products < 2^30, so every residual
+            // fits a signed word); each sign bit is one comparison, their sum is how far the descent moves
+            // (0, h, m or m+h nodes), the new R is the smallest non-negative residual = the UNSIGNED minimum of all of
+            // them, the new N the largest negative one = the unsigned maximum.  Round 2's form -- compare, select the
+            // second boundary, compare, select the index -- paid two predicate latencies (13 cycles each) per round on
+            // the chain; here a round is IMAD, SHF, IADD3, IMAD between two table loads.
+            const uint32_t nrange = ~rm1;                     // -(range): range = rm1 + 1
+            uint32_t R = (uint32_t)X;
+            uint32_t N = (uint32_t)X - (uint32_t)C::mulr(count - eof_freq, rm1);   // node 256
+            is_eof = (int32_t)N >= 0;
+            uint32_t J = tab.pos0();
+            int kc = 0;
+#pragma unroll
+            for (int m = 128; m >= 2; m >>= 2) {
+                const int h = m >> 1;
+                const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;      // nodes i+1, i+3 are odd
+                const bool cached = m == 128;
+                // position = J + kc entries: J (a byte address, LaneTable2::pos0) collects the data-dependent steps --
+                // each round moves back from its far end i + m + h by up to three half-steps -- and kc the constants,
+                // which fold into the loads' immediate offsets
+                constexpr int EB = (int)sizeof(TW);                            // bytes per table entry
+                const uint32_t ia = J + (uint32_t)((kc + (m << 5)) * EB), ib = J + (uint32_t)((kc + (h << 5) + oddadj) * EB),
+                               ic = J + (uint32_t)((kc + ((m + h) << 5) + oddadj) * EB);
+                const uint32_t ar = cached ? top_a : tab.ld_at(ia);
+                const uint32_t br = cached ? top_b : tab.ld_at(ib);
+                const uint32_t cr = cached ? top_c : tab.ld_at(ic);
+                const uint32_t da = ((FULL ? 0u : (uint32_t)m) + ar) * nrange + R;
+                const uint32_t db = ((FULL ? 0u : (uint32_t)h) + br) * nrange + R;
+                const uint32_t dc = ((FULL ? 0u : (uint32_t)h) + cr) * nrange + da;
+                // -1: the boundary lies above X, the descent turns left there
+                const uint32_t ma = (uint32_t)((int32_t)da >> 31), mb = (uint32_t)((int32_t)db >> 31), mc = (uint32_t)((int32_t)dc >> 31);
+                if (UPD) {
+                    // a left turn = the node covers the symbol from above = it is on the symbol's update path
+                    // (node c only when the first level went right: ma = -1 implies mc = -1, so that is mc - ma);
+                    // stored unconditionally: value + 0 or + 1
+                    if (cached) { top_a -= ma; top_b -= mb; top_c -= mc - ma; }
+                    else {
+                        tab.st_at(ia, ar - ma);
+                        tab.st_at(ib, br - mb);
+                        tab.st_at(ic, cr - mc + ma);
+                    }
+                }
+                R = umin32(umin32(R, db), umin32(da, dc));
+                N = umax32(umax32(N, db), umax32(da, dc));
+                J += (ma + mb + mc) * (uint32_t)((h << 5) * EB);
+                pin_chain(J);
+                kc += 3 * (h << 5);
+            }
+            I = (J - tab.pos0() + (uint32_t)kc * (uint32_t)sizeof(TW)) / (uint32_t)sizeof(TW);
+            plo = (uint32_t)X - R;
+            phi = (uint32_t)X - N;
+        } else
+#endif
         if (CLS == kNarrow) {
             phi = C::mulr(count - eof_freq, rm1);             // node 256
             is_eof = X >= phi;
@@ -734,6 +853,44 @@ struct LaneDecoderAl {
             // negative beyond -0.775, which truncates to 0), so ONE one-sided check finishes it.
             uint32_t v = (uint32_t)fmaf(__ull2float_rn((unsigned long long)X), rcp_approx((float)rm1 + 1.0f), -0.4f);
             if (X - C::mulr(v, rm1) > (P)rm1) v += 1u;         // remainder >= range: the estimate was one too low
+#ifndef RDX_DEC_PREDICATED
+            // the residual-domain 4-ary descent of the narrow class on plain values: R = v - lo, N = v - hi < 0
+            uint32_t R = v, N = v - (count - eof_freq);
+            is_eof = (int32_t)N >= 0;                         // the quotient is in hand: no product for node 256
+            uint32_t J = tab.pos0();
+            int kc = 0;
+#pragma unroll
+            for (int m = 128; m >= 2; m >>= 2) {
+                const int h = m >> 1;
+                const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;
+                const bool cached = m == 128;
+                constexpr int EB = (int)sizeof(TW);                            // bytes per table entry
+                const uint32_t ia = J + (uint32_t)((kc + (m << 5)) * EB), ib = J + (uint32_t)((kc + (h << 5) + oddadj) * EB),
+                               ic = J + (uint32_t)((kc + ((m + h) << 5) + oddadj) * EB);
+                const uint32_t ar = cached ? top_a : tab.ld_at(ia);
+                const uint32_t br = cached ? top_b : tab.ld_at(ib);
+                const uint32_t cr = cached ? top_c : tab.ld_at(ic);
+                const uint32_t da = R - ((FULL ? 0u : (uint32_t)m) + ar);
+                const uint32_t db = R - ((FULL ? 0u : (uint32_t)h) + br);
+                const uint32_t dc = da - ((FULL ? 0u : (uint32_t)h) + cr);
+                const uint32_t ma = (uint32_t)((int32_t)da >> 31), mb = (uint32_t)((int32_t)db >> 31), mc = (uint32_t)((int32_t)dc >> 31);
+                if (UPD) {
+                    if (cached) { top_a -= ma; top_b -= mb; top_c -= mc - ma; }
+                    else {
+                        tab.st_at(ia, ar - ma);
+                        tab.st_at(ib, br - mb);
+                        tab.st_at(ic, cr - mc + ma);
+                    }
+                }
+                R = umin32(umin32(R, db), umin32(da, dc));
+                N = umax32(umax32(N, db), umax32(da, dc));
+                J += (ma + mb + mc) * (uint32_t)((h << 5) * EB);
+                pin_chain(J);
+                kc += 3 * (h << 5);
+            }
+            I = (J - tab.pos0() + (uint32_t)kc * (uint32_t)sizeof(TW)) / (uint32_t)sizeof(TW);
+            const uint32_t lo = v - R, hi = v - N;
+#else
             uint32_t lo = 0, hi = count - eof_freq;           // cum(i) <= v < hi tracked in the value domain
             is_eof = v >= hi;                                 // the quotient is in hand: no product for node 256
 #pragma unroll
@@ -765,6 +922,7 @@ struct LaneDecoderAl {
                 lo = r2 ? p2 : (ra ? a : lo);
                 I = Im + (r2 ? (uint32_t)(h << 5) : 0u);
             }
+#endif
             plo = C::mulr(lo, rm1);
             phi = C::mulr(hi, rm1);
         }
@@ -774,9 +932,9 @@ struct LaneDecoderAl {
         const uint32_t nh2 = ~((uint32_t)C::divc(phi, g, count) * one + (L - 1u));
         const uint32_t l2 = (uint32_t)C::divc(plo, g, count) * one + L;
         // src/codec.rs:140-158 in closed form
-        const uint32_t n1 = common_prefix<C32>(~(l2 ^ nh2));
-        const uint32_t k = clz_nz(~shl_c((l2 & nh2) << 1, n1));
-        const uint32_t n = n1 + k;
+        uint32_t n1, n;
+        renorm_counts<C32>(l2, nh2, n1, n);
+        const uint32_t k = n - n1;
         // ONE exit per step: the EOF symbol (src/codec.rs:136-138: no renorm, no reads), bits running out inside
         // get_bit (:49-52: Err(Eof)) or, when PEEK, a data symbol with nowhere to go
         if ((int)PEEK | (int)is_eof | (int)(n > left)) {            // bitwise: one condition, one branch

@@ -250,9 +250,9 @@ __device__ __forceinline__ void split_step(uint32_t &L, uint32_t &rm1, uint32_t 
     const uint32_t qh = (uint32_t)C::divc(nh, g, count), ql = (uint32_t)C::divc(nl, g, count);
     const uint32_t nh2 = ~(qh * one + (L - 1u));
     const uint32_t l2 = ql * one + L;
-    n1 = common_prefix<C32>(~(l2 ^ nh2));
-    k = clz_nz(~shl_c((l2 & nh2) << 1, n1));
-    const uint32_t n = n1 + k;
+    uint32_t n;
+    renorm_counts<C32>(l2, nh2, n1, n);
+    k = n - n1;
     rm1 = shl_c(qh - ql, n) - 1u;                                  // (high' - low' + 1) << n, minus one
     bits = top_bits(l2, n1);
     L = shl_c(l2, n) & 0x7FFFFFFFu;

@@ -408,9 +408,9 @@ decode_warp_al_kernel(const LaneDecJob job)
         // src/codec.rs:133-134 and :140-158 in closed form
         const uint32_t nh2 = ~((uint32_t)C::divc(C::mulr(ch, rm1), g, count) * one + (L - 1u));
         const uint32_t l2 = (uint32_t)C::divc(C::mulr(cl, rm1), g, count) * one + L;
-        const uint32_t n1 = common_prefix<C32>(~(l2 ^ nh2));
-        const uint32_t k = clz_nz(~shl_c((l2 & nh2) << 1, n1));
-        const uint32_t n = n1 + k;
+        uint32_t n1, n;
+        renorm_counts<C32>(l2, nh2, n1, n);
+        const uint32_t k = n - n1;
         if (n > left) { st = 1; left = 0; break; }                 // Err(Eof) inside get_bit (:49-52)
         if (t >= cap) { st = 6; break; }                           // sink full
         left -= n;
