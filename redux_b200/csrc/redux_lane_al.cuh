@@ -98,6 +98,22 @@ template <typename TW, bool FULL>
 struct LaneTable2 : LaneTable<TW> {
     using B = LaneTable<TW>;
     using B::t;
+    // The lane's column as (CTA's shared-memory base, byte offset of the column in it).  The offset is
+    // warp * slab + lane * 4: bits 7 and up of the slab-relative part are zero, exactly where the row of a node goes
+    // (a row = 32 lanes x 4 bytes), so `row bits | column offset` needs no addition and the shared-memory base
+    // stays in the instruction's uniform operand.
+    uint8_t *smem0;
+    uint32_t col;
+    __device__ __forceinline__ void init(void *smem, uint32_t warp, uint32_t lane) {
+        B::init(smem, warp, lane);
+        smem0 = reinterpret_cast<uint8_t *>(smem);
+        col = warp * (uint32_t)(kTabNodes * 32 * sizeof(TW)) + lane * 4u;
+#if defined(__CUDA_ARCH__)
+        // opaque: knowing that the bits are disjoint the compiler turns the OR back into an addition and folds the
+        // shared-memory base into it -- two instructions per access again
+        asm volatile("" : "+r"(col));
+#endif
+    }
 
     // init_tree != NULL: start from a model the caller trained (FULL tables only); tree[0..255] as u32
     __device__ __forceinline__ void reset(const uint32_t *init_tree = nullptr) {
@@ -159,6 +175,54 @@ struct LaneTable2 : LaneTable<TW> {
     // (cum(s), cum(s+1)) of adaptive_tree.rs:63-80 and, when UPDATE, update(s+1) of :83-92, sharing the
     // node addresses.  `cum256` = cum(256) = total - frequency of EOF (the unstored node 256; for a fresh model
     // 256 + the number of updates so far); with increments-only tables (!FULL) the caller passes it minus 256.
+#ifndef RDX_ENC_TWO_WALKS
+    // One node per tree level serves the range query AND the update.  The descent to s (adaptive_tree.rs:119-127)
+    // stands, at level k = 7..0, on node n_k = (s & (0xFF << (k+1))) + 2^k.  Where bit k of s is set it turns right:
+    // n_k = s & (0xFF << k) is a node of the prefix path of s (get_frequency_range, :63-80).  Where the bit is clear
+    // it turns left: n_k = (s | (2^k - 1)) + 1 is a node of the update path of s + 1 (:83-92).  cum(s + 1) walks the
+    // same nodes with the bits of s + 1: above the lowest clear bit k* of s the bits (and nodes) agree, bit k* is set
+    // and its node (s + 1) & (0xFF << k*) is n_k* again, the bits below are clear.  So eight loads -- round 1 loaded
+    // sixteen, a query node and an update node per level, of which one was masked off -- give both sums and the
+    // values to increment; with u16 entries both sums accumulate in one register (low half cum(s), high half
+    // cum(s+1): neither can carry, a cumulative value is at most 65,535 here).
+    template <bool UPDATE>
+    __device__ __forceinline__ void query(uint32_t s, uint32_t cum256, uint32_t &cl, uint32_t &ch) {
+        const uint32_t z = s | ((s + 1u) << 16);               // bits of s and of s + 1, 16 apart
+        TW *a[8];
+        uint32_t v[8];
+        // byte offset of node n_k in the CTA's shared memory: (row of the even node below it | column) + a constant
+        constexpr uint32_t NB = 32u * (uint32_t)sizeof(TW);    // bytes from node i to node i + 1
+        const uint32_t SB = s * NB;
+        a[0] = reinterpret_cast<TW *>(smem0 + (((SB & (0xFEu * NB)) | col) + (sizeof(TW) == 2 ? 2u : NB)));   // the odd node of s's pair
+#pragma unroll
+        for (int k = 1; k < 8; ++k)
+            a[k] = reinterpret_cast<TW *>(smem0 + (((SB & (((0xFFu << (k + 1)) & 0xFFu) * NB)) | col) + (NB << k)));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = *a[k];
+        uint32_t lo, hi;
+        if (sizeof(TW) == 2) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc += v[k] * ((z >> k) & 0x00010001u);
+            lo = acc & 0xFFFFu; hi = acc >> 16;
+        } else {                                               // (predicated adds for u16 too: measured +30 instructions)
+            lo = 0; hi = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (z & (1u << k)) lo += v[k];
+                if (z & (0x10000u << k)) hi += v[k];
+            }
+        }
+        cl = lo + (FULL ? 0u : s);
+        ch = (s == 255u ? cum256 : hi) + (FULL ? 0u : s + 1u);
+        if (UPDATE) {
+            // all loads before all stores: the nodes are distinct, which the compiler cannot know
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (!(s & (1u << k))) *a[k] = (TW)(v[k] + 1u);
+        }
+    }
+#else
     template <bool UPDATE>
     __device__ __forceinline__ void query(uint32_t s, uint32_t cum256, uint32_t &cl, uint32_t &ch) {
         const uint32_t S = s << 5;
@@ -214,6 +278,8 @@ struct LaneTable2 : LaneTable<TW> {
         }
     }
 
+#endif
+
     // update(s+1) alone (decoder: the search already produced the range)
     __device__ __forceinline__ void update(uint32_t s) {
         const uint32_t S = s << 5;
@@ -250,10 +316,11 @@ struct LaneTable2 : LaneTable<TW> {
             // C[s] sits at byte (s >> 1) * 128 + (s & 1) * 2 of the lane's column; C[s+1] two bytes further for an
             // even s, in the next word row (126 bytes further) for an odd one.  For s = 255 that is the padded row
             // after the table: loaded, never used.
+            // (row of the pair | column) + the halfword, from the CTA's shared-memory base (see `col`)
             const uint32_t odd = s & 1u;
-            const uint8_t *pb = reinterpret_cast<const uint8_t *>(t) + (((s << 6) & 0x3F80u) | (odd << 1));
+            const uint8_t *pb = smem0 + ((((s << 6) & 0x3F80u) | col) + (odd << 1));
             lo = *reinterpret_cast<const uint16_t *>(pb);
-            hi = *reinterpret_cast<const uint16_t *>(pb + (odd ? 126 : 2));
+            hi = *reinterpret_cast<const uint16_t *>(pb + odd * 124u + 2u);
         } else {
             lo = t[s << 5];
             hi = t[((s + 1) & 255u) << 5];
