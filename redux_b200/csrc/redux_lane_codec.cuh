@@ -340,6 +340,8 @@ __device__ __forceinline__ uint32_t encode_step(typename Cls<CLS>::S &low, typen
     return r.n1 + r.k;
 }
 
+template <typename TW, bool FULL> struct LaneTable2;       // redux_lane_al.cuh: one-walk query + update
+
 // ------------------------------------------------------------------ encoder
 template <typename TW, int CLS>
 __global__ void __launch_bounds__(kLaneThreads, 2)
@@ -353,7 +355,7 @@ encode_lane_kernel(const LaneEncJob job)
     const uint64_t blk = (uint64_t)blockIdx.x * kLaneThreads + threadIdx.x;
     if (blk >= job.n_blocks) return;
 
-    LaneTable<TW> tab;
+    LaneTable2<TW, false> tab;                             // increments only, as LaneTable
     tab.init(smem_u4, warp, lane);
     tab.clear();
 
@@ -380,8 +382,7 @@ encode_lane_kernel(const LaneEncJob job)
         gn = C::ldm(magic + t + 1);
         const uint32_t sym = src.next();
         uint32_t cl, ch;
-        tab.query(sym, t, cl, ch);
-        tab.update(sym);
+        tab.template query<true>(sym, t, cl, ch);          // cum(256) - 256 = the number of updates so far
         encode_step<CLS>(low, high, pend, sink, cl, ch, kNsym + t, g, c);
     }
     // frozen phase (adaptive_tree.rs:84): total == FMAX, table and reciprocal are constant
@@ -393,10 +394,10 @@ encode_lane_kernel(const LaneEncJob job)
         // The lookup does not depend on the coder state: fetch + look up symbol t+1 before
         // coding symbol t, so the shared-memory latency overlaps the range update of the previous symbol.
         uint32_t cl, ch;
-        tab.query_frozen(src.next(), countf, cl, ch);
+        tab.query_frozen(src.next(), countf - 1u, cl, ch);   // cum(256) = total - 1
         for (; t + 1 < len; ++t) {
             const uint32_t cl_cur = cl, ch_cur = ch;
-            tab.query_frozen(src.next(), countf, cl, ch);
+            tab.query_frozen(src.next(), countf - 1u, cl, ch);   // cum(256) = total - 1
             encode_step<CLS>(low, high, pend, sink, cl_cur, ch_cur, countf, gf, c);
         }
         encode_step<CLS>(low, high, pend, sink, cl, ch, countf, gf, c);
@@ -551,16 +552,22 @@ struct LaneDecoder {
                 }
             } else {
 #pragma unroll
+                // The model update rides on the descent (as in redux_lane_al.cuh): the nodes update(s+1) increments
+                // (adaptive_tree.rs:83-92) are exactly the nodes at which the descent to s turns left, and their
+                // values have just been loaded.  A step that ends the stream afterwards (EOF symbol, bits ran out,
+                // sink full) leaves a table nobody reads again.
                 for (int m = 128; m >= 2; m >>= 1) {              // even nodes i + m
-                    const uint32_t tv = (uint32_t)m + tab.t[I + (uint32_t)(m << 5)];
-                    const P p = C::mul_add(tv, rm1, plo);
+                    const uint32_t raw = tab.t[I + (uint32_t)(m << 5)];
+                    const P p = C::mul_add((uint32_t)m + raw, rm1, plo);
                     const bool right = X >= p;
+                    if (ADAPT && !right) tab.t[I + (uint32_t)(m << 5)] = (TW)(raw + 1u);
                     if (right) { I += (uint32_t)(m << 5); plo = p; } else { phi = p; }
                 }
                 {                                                 // m = 1: odd node i + 1
-                    const uint32_t tv = 1u + tab.t[(int)I + 32 + LaneTable<TW>::kOddAdj];
-                    const P p = C::mul_add(tv, rm1, plo);
+                    const uint32_t raw = tab.t[(int)I + 32 + LaneTable<TW>::kOddAdj];
+                    const P p = C::mul_add(1u + raw, rm1, plo);
                     const bool right = X >= p;
+                    if (ADAPT && !right) tab.t[(int)I + 32 + LaneTable<TW>::kOddAdj] = (TW)(raw + 1u);
                     if (right) { I += 32u; plo = p; } else { phi = p; }
                 }
             }
@@ -572,7 +579,7 @@ struct LaneDecoder {
             // src/codec.rs:133-134
             high = low + (S)C::divc(phi, g, count) - 1;
             low = low + (S)C::divc(plo, g, count);
-            if (ADAPT) tab.update(sym);
+            if (ADAPT && CLS == kNarrow) tab.update(sym);         // (the narrow rounds above keep the separate walk)
             // src/codec.rs:140-158 in closed form
             const Renorm<S> r = renorm<S>(low, high, c);
             const uint32_t n = r.n1 + r.k;
