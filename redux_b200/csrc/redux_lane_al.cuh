@@ -764,6 +764,8 @@ struct LaneDecoderAl {
     using C = Cls<CLS>;
     using P = typename C::P;
     using M = typename C::M;
+    // narrow class: once the model is frozen the table is the cumulative array (searched with absolute boundaries)
+    static constexpr bool kFrozenCum = CLS == kNarrow && FULL && sizeof(TW) == 2;
     LaneTable2<TW, FULL> tab;
     BitWindow bw;
     ByteSinkF out;
@@ -793,6 +795,50 @@ struct LaneDecoderAl {
         P plo = 0, phi = 0;
         uint32_t I = 0;                                       // i * 32: the descent's position, in table entries
         bool is_eof;                                          // value >= cum(256) = count - freq(EOF): the EOF symbol
+#ifndef RDX_DEC_FROZEN_TREE
+        if (kFrozenCum && !ADAPT) {
+            // Frozen model, narrow class: the table has been rewritten as the cumulative array C[i] = cum(i) of
+            // AdaptiveLinearModel (adaptive_linear.rs:26-28; freeze_to_cumulative) and get_symbol (:61-70) is a 4-ary
+            // search on ABSOLUTE boundaries: the residuals X - C[.] * range of a round's three boundaries do not
+            // depend on each other or on earlier rounds, their sign bits move the position, and nothing else is
+            // tracked -- the symbol's own two boundaries C[s], C[s+1] are looked up once at the end (the tree
+            // descent had to carry the lower and the upper product through every round: four min / max operations
+            // per round).  Entry i sits where tree node i sat: halfword i & 1 of the lane's word i >> 1.
+            const uint32_t nrange = ~rm1;                     // -(range)
+            const uint32_t Xr = (uint32_t)X;
+            is_eof = Xr >= (uint32_t)C::mulr(count - eof_freq, rm1);
+            uint32_t J = tab.pos0();                          // data-dependent part of the position (a byte address)
+            int kb = 0;                                       // constant part, folded into the loads' offsets
+#pragma unroll
+            for (int h = 64; h >= 4; h >>= 2) {               // entries i + h, i + 2h, i + 3h (even: 64 bytes per entry)
+                const bool cached = h == 64;
+                const uint32_t vb = cached ? top_b : tab.ld_at(J + (uint32_t)(kb + h * 64));
+                const uint32_t va = cached ? top_a : tab.ld_at(J + (uint32_t)(kb + 2 * h * 64));
+                const uint32_t vc = cached ? top_c : tab.ld_at(J + (uint32_t)(kb + 3 * h * 64));
+                // -1: the boundary lies above X.  The search stands at the far end i + 3h and moves back
+                const uint32_t ma = (uint32_t)((int32_t)(va * nrange + Xr) >> 31), mb = (uint32_t)((int32_t)(vb * nrange + Xr) >> 31),
+                               mc = (uint32_t)((int32_t)(vc * nrange + Xr) >> 31);
+                J += (ma + mb + mc) * (uint32_t)(h * 64);
+                pin_chain(J);
+                kb += 3 * h * 64;
+            }
+            // last round: entries i + 1, i + 2, i + 3 at bytes +2, +128, +130 of entry i (i is a multiple of four)
+            const uint32_t vb = tab.ld_at(J + (uint32_t)(kb + 2)), va = tab.ld_at(J + (uint32_t)(kb + 128)), vc = tab.ld_at(J + (uint32_t)(kb + 130));
+            const uint32_t ma = (uint32_t)((int32_t)(va * nrange + Xr) >> 31), mb = (uint32_t)((int32_t)(vb * nrange + Xr) >> 31),
+                           mc = (uint32_t)((int32_t)(vc * nrange + Xr) >> 31);
+            // the masks turn on in the order c, a, b as X falls: byte 130, 128, 2, 0 of the group
+            J += 2u * (mb + mc) + 126u * ma;
+            pin_chain(J);
+            kb += 130;
+            const uint32_t odd = (ma + mb + mc + 1u) & 1u;    // s = i + 3 + (ma + mb + mc)
+            const uint32_t lo = tab.ld_at(J + (uint32_t)kb);
+            const uint32_t hi = tab.ld_at(J + (uint32_t)kb + 2u + 124u * odd);        // next halfword / next word
+            const uint32_t B = J - tab.pos0() + (uint32_t)kb; // byte (s >> 1) * 128 + (s & 1) * 2 of the column
+            I = ((B >> 6) | odd) << 5;
+            plo = C::mulr(lo, rm1);
+            phi = C::mulr(I == (255u << 5) ? count - eof_freq : hi, rm1);
+        } else
+#endif
 #ifndef RDX_DEC_PREDICATED
         if (CLS == kNarrow) {
             // 4-ary descent in the RESIDUAL domain, without a single predicate.  R = X - (largest boundary known to
@@ -1122,6 +1168,9 @@ decode_lane_al_kernel(const LaneDecJob job)
     d.template run<true, false>(e1, magic, 0, g0);
     if (d.st == 0 && d.t == cap && cap < tcap) d.template run<true, true>(d.t + 1, magic, 0, g0);
     const M gf = D::C::mk(job.gf_m, job.gf_sh);               // reciprocal of FMAX: launch constants, no global load
+#ifndef RDX_DEC_FROZEN_TREE
+    if (D::kFrozenCum && d.st == 0) d.tab.freeze_to_cumulative();   // a frozen step will run (at least the peek)
+#endif
     d.template run<false, false>(d.st != 0 ? d.t : cap, magic, d.count0 + tcap, gf);
     if (d.st == 0) d.template run<false, true>(d.t + 1, magic, d.count0 + tcap, gf);
     d.out.finish(scratch);
