@@ -642,6 +642,15 @@ def test_multi_device_context_shards_by_block_ranges():
             assert (st == 0).all() and (cons == coff[1:] - coff[:-1]).all()
             if params[0] == 8:
                 assert (rl == lens).all() and (back[: int(off[-1])] == data).all()
+            # the same through the pageable-memory staging (feeder thread + ring per device, shard hand-off between
+            # the drainers): forced on with pieces small enough to wrap the rings many times
+            many.set_staging(True, min_bytes=1, piece_bytes=4096 * 5, slots=3, threads=3)
+            comp2, coff2, st2 = many.encode_batch(data, off, model)
+            assert comp2.tobytes() == ref_comp.tobytes() and (coff2 == ref_off).all() and (st2 == 0).all()
+            back2, rl2, cons2, st2 = many.decode_batch(comp2, coff2, off, model)
+            assert (st2 == 0).all() and (rl2 == rl).all() and (cons2 == cons).all()
+            if params[0] == 8:
+                assert (back2[: int(off[-1])] == data).all()
         for i in (0, 1, 2, 1500, 3000):
             b = data[int(off[i]):int(off[i + 1])]
             want = o.compress_trained(b, train, o.TREE, params)[1] if trained else o.compress(b, o.TREE, params)[1]
