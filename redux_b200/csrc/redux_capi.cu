@@ -292,9 +292,9 @@ struct Plan {
     uint64_t max_len = 0;   // longest block of the launch
 };
 
-// REDUX_SCHED_AUTO, encode: below this many streams the split encoder (parallel model phase + one coder warp per
+// REDUX_SCHED_AUTO, encode: up to this many streams the split encoder (parallel model phase + one coder warp per
 // stream) beats 32 streams per warp (profiles/r02_small_batches_corpora.json, profiles/r02_underfilled.json: 512
-// blocks of 64 KiB encode in 7.6 ms split vs 9.6 ms lane; 2,048 blocks 19.7 vs 9.8 ms).  The plain warp encoder never
+// blocks of 64 KiB encode in 7.1 ms split vs 8.8 ms lane, 9.7 vs 14.0 ms at (8,30,32); 2,048 blocks 19.5 vs 9.2 ms).  The plain warp encoder never
 // wins (29 corpus files: 31 MB/s against 62 lane and 86 split), so AUTO falls back to the lane mapping, not to it.
 constexpr uint64_t kWarpAutoMaxBlocks = 512;
 
@@ -318,7 +318,7 @@ constexpr uint64_t kSplitMaxPairBytes = (uint64_t)2 << 30;
 bool choose_split(const redux_ctx *ctx, uint64_t n_blocks, int cls, uint64_t max_len)
 {
     if (ctx->sched == REDUX_SCHED_LANE || ctx->sched == REDUX_SCHED_WARP) return false;
-    if (ctx->sched == REDUX_SCHED_AUTO && n_blocks >= kWarpAutoMaxBlocks) return false;
+    if (ctx->sched == REDUX_SCHED_AUTO && n_blocks > kWarpAutoMaxBlocks) return false;
     if (cls == kHuge || max_len == 0) return false;
     const uint64_t stride = (max_len + 31) & ~(uint64_t)31;
     return n_blocks * stride * sizeof(uint2) <= kSplitMaxPairBytes;
