@@ -544,9 +544,6 @@ encode_lane_al_kernel(const LaneEncJob job)
     while (t < n_adapt && !src.word_aligned()) adapt_step(src.next());
     if (t + 4 <= n_adapt) {
         M g0 = gn, g1 = C::ldm(magic + t + 1), g2 = C::ldm(magic + t + 2), g3 = C::ldm(magic + t + 3);
-#ifdef RDX_UNROLL2
-#pragma unroll 2
-#endif
         while (t + 4 <= n_adapt) {
             const M m0 = C::ldm(magic + t + 4), m1 = C::ldm(magic + t + 5), m2 = C::ldm(magic + t + 6), m3 = C::ldm(magic + t + 7);
             const uint32_t wv = src.take_word();
