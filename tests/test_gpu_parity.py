@@ -142,7 +142,8 @@ def test_empty_and_tiny_blocks(ctx):
 
 
 @pytest.mark.parametrize("params", TRIPLES + [(8, 10, 12), (8, 10, 16), (8, 12, 18), (8, 16, 18), (8, 20, 22),
-                                              (8, 24, 30), (8, 17, 32), (8, 30, 34), (8, 20, 44), (8, 10, 54)])
+                                              (8, 24, 30), (8, 17, 32), (8, 30, 34), (8, 20, 44), (8, 10, 54),
+                                              (8, 10, 30), (8, 12, 32)])      # wide classes that freeze early
 def test_ragged_mixed_entropy_batch(ctx, params):
     """Ragged lengths (0..5000), every generator class, both model kinds; freeze regime for small f."""
     rng = np.random.default_rng(params[1] * 100 + params[2])
