@@ -175,7 +175,6 @@ struct LaneTable2 : LaneTable<TW> {
     // (cum(s), cum(s+1)) of adaptive_tree.rs:63-80 and, when UPDATE, update(s+1) of :83-92, sharing the
     // node addresses.  `cum256` = cum(256) = total - frequency of EOF (the unstored node 256; for a fresh model
     // 256 + the number of updates so far); with increments-only tables (!FULL) the caller passes it minus 256.
-#ifndef RDX_ENC_TWO_WALKS
     // One node per tree level serves the range query AND the update.  The descent to s (adaptive_tree.rs:119-127)
     // stands, at level k = 7..0, on node n_k = (s & (0xFF << (k+1))) + 2^k.  Where bit k of s is set it turns right:
     // n_k = s & (0xFF << k) is a node of the prefix path of s (get_frequency_range, :63-80).  Where the bit is clear
@@ -222,63 +221,6 @@ struct LaneTable2 : LaneTable<TW> {
                 if (!(s & (1u << k))) *a[k] = (TW)(v[k] + 1u);
         }
     }
-#else
-    template <bool UPDATE>
-    __device__ __forceinline__ void query(uint32_t s, uint32_t cum256, uint32_t &cl, uint32_t &ch) {
-        const uint32_t S = s << 5;
-        const uint32_t bothmask = s & (s + 1);                 // set bits above the lowest zero bit
-        const uint32_t q = ~s & 255u;                          // clear bits of s
-        const uint32_t levels = q ^ __funnelshift_rc(0x80000000u, 0u, clz_sh(q));   // minus the one that leads to node 256
-        TW *a[8];
-        uint32_t v[8];
-#pragma unroll
-        for (int b = 1; b < 8; ++b) {
-            a[b] = t + (S & (0x1FE0u << b));                   // even node s & (0xFF << b)
-            v[b] = *a[b];
-        }
-        TW *po = t + B::node_index(s | 1u);                    // the odd node of s's pair
-        TW *pn = t + B::node_index(((s | 1u) + 1u) & 255u);    // the even node after it (node 0 when it is 256)
-        const uint32_t xo = *po, xn = *pn;
-        const bool odd = s & 1u, last = s == 255u;
-        uint32_t total, both;
-        if (sizeof(TW) == 2) {
-            // both sums in one register: `total` in the low half, `both` in the high half.  Level b adds
-            // v[b] * W with W = (bit b of s) + (bit b of bothmask) << 16 -- one multiply-add per level instead
-            // of two masked adds.  Neither half can carry: a path sum is at most cum(s) <= 65,535 here.
-            const uint32_t z = s | (bothmask << 16);
-            uint32_t acc = 0;
-#pragma unroll
-            for (int b = 1; b < 8; ++b) acc += v[b] * ((z >> b) & 0x00010001u);
-            total = (acc & 0xFFFFu) + (odd ? xo : 0u);
-            both = acc >> 16;
-        } else {
-            total = odd ? xo : 0u; both = 0;
-#pragma unroll
-            for (int b = 1; b < 8; ++b) {
-                total += (s & (1u << b)) ? v[b] : 0u;
-                both += (bothmask & (1u << b)) ? v[b] : 0u;
-            }
-        }
-        const uint32_t top = odd ? (last ? cum256 : xn) : xo;
-        cl = total + (FULL ? 0u : s);
-        ch = top + both + (FULL ? 0u : s + 1u);
-        if (UPDATE) {
-            // all loads before all stores: the nodes of one update path are distinct, which the compiler
-            // cannot know, and a load/store/load/store chain would serialise the shared-memory round trips
-            uint32_t u[8];
-#pragma unroll
-            for (int k = 1; k < 8; ++k)                        // (s | (2^k - 1)) + 1 = (s & (0xFF << k)) + 2^k
-                u[k] = a[k][32 << k];                          // unconditional: "node 256" is the row after
-                                                               // the warp's table (padded, kTabPadBytes)
-            // node s+1 (the odd node for even s, the following even node for odd s; node 256 unstored)
-            if (!last) { TW *p = odd ? pn : po; *p = (TW)((odd ? xn : xo) + 1u); }
-#pragma unroll
-            for (int k = 1; k < 8; ++k)
-                if (levels & (1u << (k - 1))) a[k][32 << k] = (TW)(u[k] + 1u);
-        }
-    }
-
-#endif
 
     // update(s+1) alone (decoder: the search already produced the range)
     __device__ __forceinline__ void update(uint32_t s) {
@@ -412,7 +354,7 @@ struct StageSlot {
 // this thread's slot: the CTA's slots follow its kLaneWarpsPerCta tables (kTabPadBytes)
 template <typename TW>
 __device__ __forceinline__ void *lane_stage_slot(void *smem) {
-    return reinterpret_cast<uint8_t *>(smem) + (size_t)kLaneWarpsPerCta * kTabNodes * 32 * sizeof(TW) + threadIdx.x * 4;
+    return reinterpret_cast<uint8_t *>(smem) + (size_t)kLaneWarpsPerCta * kTabNodes * 32 * sizeof(TW) + kTabZeroRowBytes + threadIdx.x * 4;
 }
 
 // ------------------------------------------------------------------ byte source (encoder input), v3
@@ -795,18 +737,19 @@ struct LaneDecoderAl {
         P plo = 0, phi = 0;
         uint32_t I = 0;                                       // i * 32: the descent's position, in table entries
         bool is_eof;                                          // value >= cum(256) = count - freq(EOF): the EOF symbol
-#ifndef RDX_DEC_FROZEN_TREE
         if (kFrozenCum && !ADAPT) {
             // Frozen model, narrow class: the table has been rewritten as the cumulative array C[i] = cum(i) of
             // AdaptiveLinearModel (adaptive_linear.rs:26-28; freeze_to_cumulative) and get_symbol (:61-70) is a 4-ary
             // search on ABSOLUTE boundaries: the residuals X - C[.] * range of a round's three boundaries do not
             // depend on each other or on earlier rounds, their sign bits move the position, and nothing else is
-            // tracked -- the symbol's own two boundaries C[s], C[s+1] are looked up once at the end (the tree
-            // descent had to carry the lower and the upper product through every round: four min / max operations
-            // per round).  Entry i sits where tree node i sat: halfword i & 1 of the lane's word i >> 1.
+            // tracked until the last round, which fetches its whole group of five entries and takes the symbol's two
+            // boundaries from their residuals (the tree descent had to carry the lower and the upper product through
+            // every round: four min / max operations per round).  Entry i sits where tree node i sat: halfword
+            // i & 1 of the lane's word i >> 1.
             const uint32_t nrange = ~rm1;                     // -(range)
             const uint32_t Xr = (uint32_t)X;
-            is_eof = Xr >= (uint32_t)C::mulr(count - eof_freq, rm1);
+            const uint32_t N0 = Xr - (uint32_t)C::mulr(count - eof_freq, rm1);       // X - cum(256) * range
+            is_eof = (int32_t)N0 >= 0;
             uint32_t J = tab.pos0();                          // data-dependent part of the position (a byte address)
             int kb = 0;                                       // constant part, folded into the loads' offsets
 #pragma unroll
@@ -822,24 +765,23 @@ struct LaneDecoderAl {
                 pin_chain(J);
                 kb += 3 * h * 64;
             }
-            // last round: entries i + 1, i + 2, i + 3 at bytes +2, +128, +130 of entry i (i is a multiple of four)
-            const uint32_t vb = tab.ld_at(J + (uint32_t)(kb + 2)), va = tab.ld_at(J + (uint32_t)(kb + 128)), vc = tab.ld_at(J + (uint32_t)(kb + 130));
-            const uint32_t ma = (uint32_t)((int32_t)(va * nrange + Xr) >> 31), mb = (uint32_t)((int32_t)(vb * nrange + Xr) >> 31),
-                           mc = (uint32_t)((int32_t)(vc * nrange + Xr) >> 31);
-            // the masks turn on in the order c, a, b as X falls: byte 130, 128, 2, 0 of the group
-            J += 2u * (mb + mc) + 126u * ma;
-            pin_chain(J);
-            kb += 130;
-            const uint32_t odd = (ma + mb + mc + 1u) & 1u;    // s = i + 3 + (ma + mb + mc)
-            const uint32_t lo = tab.ld_at(J + (uint32_t)kb);
-            const uint32_t hi = tab.ld_at(J + (uint32_t)kb + 2u + 124u * odd);        // next halfword / next word
-            const uint32_t B = J - tab.pos0() + (uint32_t)kb; // byte (s >> 1) * 128 + (s & 1) * 2 of the column
-            I = ((B >> 6) | odd) << 5;
-            plo = C::mulr(lo, rm1);
-            phi = C::mulr(I == (255u << 5) ? count - eof_freq : hi, rm1);
+            // last round: the whole group C[i .. i+4] (i is a multiple of four: bytes +0, +2, +128, +130, +256 of entry
+            // i) in ONE round trip.  Its residuals are ordered, d0 >= d1 >= ... >= d4, with d0 >= 0; the symbol's lower
+            // boundary is the one with the smallest non-negative residual (the unsigned minimum), its upper boundary
+            // the one with the largest negative residual (the unsigned maximum -- N0 = X - cum(256) * range, negative
+            // for every data symbol, stands in for C[256], which the table does not hold: "entry 256" reads a zero,
+            // see kTabZeroRowBytes, whose residual X is non-negative and so never the maximum).
+            const uint32_t e0 = tab.ld_at(J + (uint32_t)kb), e1 = tab.ld_at(J + (uint32_t)(kb + 2)), e2 = tab.ld_at(J + (uint32_t)(kb + 128)),
+                           e3 = tab.ld_at(J + (uint32_t)(kb + 130)), e4 = tab.ld_at(J + (uint32_t)(kb + 256));
+            const uint32_t d0 = e0 * nrange + Xr, d1 = e1 * nrange + Xr, d2 = e2 * nrange + Xr, d3 = e3 * nrange + Xr, d4 = e4 * nrange + Xr;
+            const uint32_t R = umin32(umin32(d0, d1), umin32(d2, d3));
+            const uint32_t N = umax32(umax32(N0, d1), umax32(umax32(d2, d3), d4));
+            // s = i + the number of boundaries C[i+1 .. i+3] at or below X
+            const uint32_t cnt = 3u + (uint32_t)((int32_t)d1 >> 31) + (uint32_t)((int32_t)d2 >> 31) + (uint32_t)((int32_t)d3 >> 31);
+            I = (((J - tab.pos0() + (uint32_t)kb) >> 6) + cnt) << 5;      // entry i sits at byte (i >> 1) * 128
+            plo = Xr - R;
+            phi = Xr - N;
         } else
-#endif
-#ifndef RDX_DEC_PREDICATED
         if (CLS == kNarrow) {
             // 4-ary descent in the RESIDUAL domain, without a single predicate.  R = X - (largest boundary known to
             // be <= X) and N = X - (smallest boundary known to be > X, two's complement: negative).  A round forms the
@@ -895,44 +837,7 @@ struct LaneDecoderAl {
             plo = (uint32_t)X - R;
             phi = (uint32_t)X - N;
         } else
-#endif
-        if (CLS == kNarrow) {
-            phi = C::mulr(count - eof_freq, rm1);             // node 256
-            is_eof = X >= phi;
-            // two tree levels per round (adaptive_tree.rs:119-127 unrolled by two): the candidates i+m,
-            // i+m/2 and i+m+m/2 are loaded together -- 4 dependent shared-memory round trips, not 8
-#pragma unroll
-            for (int m = 128; m >= 2; m >>= 2) {
-                const int h = m >> 1;
-                const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;      // nodes i+1, i+3 are odd
-                // (caching the twelve possible nodes of the second round as well was measured slower: 28.7 vs 27.4 ms)
-                const bool cached = m == 128;
-                const uint32_t ar = cached ? top_a : (uint32_t)tab.t[I + (uint32_t)(m << 5)];
-                const uint32_t br = cached ? top_b : (uint32_t)tab.t[(int)I + (h << 5) + oddadj];
-                const uint32_t cr = cached ? top_c : (uint32_t)tab.t[(int)I + ((m + h) << 5) + oddadj];
-                const P pa = C::mul_add((FULL ? 0u : (uint32_t)m) + ar, rm1, plo);
-                const P pb = C::mul_add((FULL ? 0u : (uint32_t)h) + br, rm1, plo);
-                const P pc = C::mul_add((FULL ? 0u : (uint32_t)h) + cr, rm1, pa);
-                const bool ra = X >= pa;                                        // first-level decision
-                const P p2 = ra ? pc : pb;                                      // second-level boundary
-                const bool r2 = X >= p2;                                        // second-level decision
-                const uint32_t Im = I + (ra ? (uint32_t)(m << 5) : 0u);         // the node the second level starts from
-                if (UPD) {
-                    // a left turn = the node covers the symbol from above = it is on the symbol's update path
-                    const uint32_t v2 = (ra ? cr : br) + 1u;
-                    if (cached) {
-                        if (!ra) top_a += 1u;
-                        if (!r2) { if (ra) top_c = v2; else top_b = v2; }
-                    } else {
-                        if (!ra) tab.t[I + (uint32_t)(m << 5)] = (TW)(ar + 1u);
-                        if (!r2) tab.t[(int)Im + (h << 5) + oddadj] = (TW)v2;
-                    }
-                }
-                phi = r2 ? (ra ? phi : pa) : p2;
-                plo = r2 ? p2 : (ra ? pa : plo);
-                I = Im + (r2 ? (uint32_t)(h << 5) : 0u);
-            }
-        } else if (CLS == kWide && count > kQuotientMaxCount) {          // (WIDE_D: totals stay below 2^17)
+        if (CLS == kWide && count > kQuotientMaxCount) {          // (WIDE_D: totals stay below 2^17)
             // 64-bit products, very long streams: the plain product-domain descent
             phi = C::mulr(count - eof_freq, rm1);
             is_eof = X >= phi;
@@ -966,7 +871,6 @@ struct LaneDecoderAl {
             // negative beyond -0.775, which truncates to 0), so ONE one-sided check finishes it.
             uint32_t v = (uint32_t)fmaf(__ull2float_rn((unsigned long long)X), rcp_approx((float)rm1 + 1.0f), -0.4f);
             if (X - C::mulr(v, rm1) > (P)rm1) v += 1u;         // remainder >= range: the estimate was one too low
-#ifndef RDX_DEC_PREDICATED
             // the residual-domain 4-ary descent of the narrow class on plain values: R = v - lo, N = v - hi < 0
             uint32_t R = v, N = v - (count - eof_freq);
             is_eof = (int32_t)N >= 0;                         // the quotient is in hand: no product for node 256
@@ -1003,39 +907,6 @@ struct LaneDecoderAl {
             }
             I = (J - tab.pos0() + (uint32_t)kc * (uint32_t)sizeof(TW)) / (uint32_t)sizeof(TW);
             const uint32_t lo = v - R, hi = v - N;
-#else
-            uint32_t lo = 0, hi = count - eof_freq;           // cum(i) <= v < hi tracked in the value domain
-            is_eof = v >= hi;                                 // the quotient is in hand: no product for node 256
-#pragma unroll
-            for (int m = 128; m >= 2; m >>= 2) {
-                const int h = m >> 1;
-                const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;
-                const bool cached = m == 128;
-                const uint32_t ar = cached ? top_a : (uint32_t)tab.t[I + (uint32_t)(m << 5)];
-                const uint32_t br = cached ? top_b : (uint32_t)tab.t[(int)I + (h << 5) + oddadj];
-                const uint32_t cr = cached ? top_c : (uint32_t)tab.t[(int)I + ((m + h) << 5) + oddadj];
-                const uint32_t a = lo + (FULL ? 0u : (uint32_t)m) + ar;
-                const uint32_t b = lo + (FULL ? 0u : (uint32_t)h) + br;
-                const uint32_t cc = a + (FULL ? 0u : (uint32_t)h) + cr;
-                const bool ra = v >= a;
-                const uint32_t p2 = ra ? cc : b;
-                const bool r2 = v >= p2;
-                const uint32_t Im = I + (ra ? (uint32_t)(m << 5) : 0u);
-                if (UPD) {
-                    const uint32_t v2 = (ra ? cr : br) + 1u;
-                    if (cached) {
-                        if (!ra) top_a += 1u;
-                        if (!r2) { if (ra) top_c = v2; else top_b = v2; }
-                    } else {
-                        if (!ra) tab.t[I + (uint32_t)(m << 5)] = (TW)(ar + 1u);
-                        if (!r2) tab.t[(int)Im + (h << 5) + oddadj] = (TW)v2;
-                    }
-                }
-                hi = r2 ? (ra ? hi : a) : p2;
-                lo = r2 ? p2 : (ra ? a : lo);
-                I = Im + (r2 ? (uint32_t)(h << 5) : 0u);
-            }
-#endif
             plo = C::mulr(lo, rm1);
             phi = C::mulr(hi, rm1);
         }
@@ -1129,10 +1000,19 @@ decode_lane_al_kernel(const LaneDecJob job)
     extern __shared__ uint4 smem_u4[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t blk = (uint64_t)blockIdx.x * kLaneThreads + threadIdx.x;
-    if (blk >= job.n_blocks) return;
-
     D d;
     d.tab.init(smem_u4, warp, lane);
+    if (D::kFrozenCum) {
+        // "Entry 256" of a frozen cumulative array is read as the halfword after the table: node 0 / C[0] of the same
+        // lane of the NEXT warp, or the zero row after the last warp's table (kTabZeroRowBytes).  It must read zero
+        // whatever that thread is doing -- also when it has no block at all, or has not started yet -- so every
+        // thread of the CTA clears it here, before the first one can get that far.
+        reinterpret_cast<uint32_t *>(d.tab.t)[0] = 0u;
+        if (warp == kLaneWarpsPerCta - 1)
+            reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem_u4) + (size_t)kLaneWarpsPerCta * kTabNodes * 32 * sizeof(TW))[lane] = 0u;
+        __syncthreads();
+    }
+    if (blk >= job.n_blocks) return;
     d.tab.reset(job.init_tree);
 
     const uint64_t coff = job.comp_off[blk];
@@ -1168,9 +1048,7 @@ decode_lane_al_kernel(const LaneDecJob job)
     d.template run<true, false>(e1, magic, 0, g0);
     if (d.st == 0 && d.t == cap && cap < tcap) d.template run<true, true>(d.t + 1, magic, 0, g0);
     const M gf = D::C::mk(job.gf_m, job.gf_sh);               // reciprocal of FMAX: launch constants, no global load
-#ifndef RDX_DEC_FROZEN_TREE
     if (D::kFrozenCum && d.st == 0) d.tab.freeze_to_cumulative();   // a frozen step will run (at least the peek)
-#endif
     d.template run<false, false>(d.st != 0 ? d.t : cap, magic, d.count0 + tcap, gf);
     if (d.st == 0) d.template run<false, true>(d.t + 1, magic, d.count0 + tcap, gf);
     d.out.finish(scratch);

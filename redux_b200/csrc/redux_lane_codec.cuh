@@ -37,7 +37,12 @@ constexpr int kTabNodes = 256;                      // nodes 0..255 (node 0 stay
 // serve as the padded row the tuned kernels' unconditional load of the update path's "node 256" falls into
 // (never stored).  2 x (7 x 16 KiB + 896 B + 1 KiB reserved per CTA) = 233,216 B of the SM's 233,472: two CTAs
 // per SM, and not a byte to spare for a second slot.
-constexpr int kTabPadBytes = kLaneThreads * 4;
+// Before the slots: one ZERO ROW (128 B).  The frozen narrow decoder (redux_lane_al.cuh) reads entry 256 of its
+// cumulative array as "the word after the table": for warps 0..5 that is row 0 of the next warp's table, whose low
+// halfword is node 0 / C[0] = 0 in every phase, for the last warp it is this row.  With it the two CTAs fill the
+// SM's 233,472 bytes exactly.
+constexpr int kTabZeroRowBytes = 128;
+constexpr int kTabPadBytes = kTabZeroRowBytes + kLaneThreads * 4;
 
 struct LaneEncJob {
     const uint8_t *in;          // raw bytes

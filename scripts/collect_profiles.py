@@ -30,11 +30,14 @@ shutil.copy(G("launches.csv"), P("ncu_launches.csv"))
 open(P("shared_memory_wavefronts.md"), "w").write(run(sys.executable, "scripts/ncu_shared_wavefronts.py", G("prof.ncu-rep")).stdout)
 
 # ---- bench records
+# (a scripts/final_short.sh visit leaves only the first two)
 for src, dst in (("bench_default.json", "bench_default.json"), ("bench_reference.json", "bench_reference_arm.json"),
                  ("bench_huge.json", "bench_code_bits_34_16384_blocks.json")):
-    json.dump(last_json(G(src)), open(P(dst), "w"), indent=1)
+    if os.path.exists(G(src)):
+        json.dump(last_json(G(src)), open(P(dst), "w"), indent=1)
 for src, dst in (("generic.json", "generic_path.json"), ("underfilled.json", "underfilled.json"), ("small.json", "small_batches_corpora.json")):
-    shutil.copy(G(src), P(dst))
+    if os.path.exists(G(src)):
+        shutil.copy(G(src), P(dst))
 if os.path.exists(os.path.join(ROOT, "gpurun_out", "bench_alignment.json")):
     shutil.copy(os.path.join(ROOT, "gpurun_out", "bench_alignment.json"), P("alignment.json"))
 shutil.copy(G("gpu.txt"), P("box.txt"))

@@ -28,6 +28,7 @@ struct EmuIdx { unsigned x, y, z; };
 extern thread_local EmuIdx threadIdx, blockIdx, blockDim, gridDim;
 
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline void __syncthreads() {}      // the emulation runs the threads of a CTA one after another
 
 static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel)
 {

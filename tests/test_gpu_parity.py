@@ -658,6 +658,27 @@ def test_multi_device_context_shards_by_block_ranges():
             assert comp[int(coff[i]):int(coff[i + 1])].tobytes() == want, (params, i)
 
 
+def test_frozen_decoder_next_to_threads_without_a_block():
+    """The frozen narrow decoder reads "entry 256" of its cumulative array from the neighbouring warp's column (or the
+    zero row after the last table).  That halfword must read zero also when the neighbouring threads have no block
+    (partially filled last CTA / warp) and the shared memory still holds another kernel's data: blocks long enough to
+    freeze, full of the symbols 252..255 whose group touches entry 256, in counts that leave warps and lanes idle."""
+    rng = np.random.default_rng(256)
+    params = (8, 10, 12)                                      # freezes after 766 symbols
+    model = rb.AdaptiveTreeModel(rb.Parameters(*params))
+    with rb.Context([0]) as c:
+        c.set_schedule(rb.SCHED_LANE)
+        for n in (1, 33, 224 + 96, 224 * 3 + 129):
+            blocks = [bytes(rng.integers(248, 256, 3000, dtype=np.uint8)) for _ in range(n)]
+            data, off = concat(blocks)
+            comp, coff, st = c.encode_batch(data, off, model)            # leaves its tables in shared memory
+            assert (st == 0).all()
+            back, rl, cons, st = c.decode_batch(comp, coff, off, model)
+            assert (st == 0).all() and (rl == 3000).all() and back.tobytes() == data.tobytes(), n
+            for i in (0, n - 1):
+                assert comp[int(coff[i]):int(coff[i + 1])].tobytes() == o.compress(blocks[i], o.TREE, params)[1]
+
+
 def test_million_symbol_block_crosses_the_quotient_bound(ctx):
     """A 1.15 MB block with a late freeze: the total frequency passes 2^20, where the 64-bit-product decoders
     stop trusting the float estimate of value = X / range (lane: product-domain descent; warp: exact 64-bit
