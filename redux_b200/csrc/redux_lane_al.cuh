@@ -310,6 +310,27 @@ struct BitSink2 {
         }
         return (emit ? 0u : pend) + k;
     }
+    // Two symbols' codes through ONE append.  Symbol A emits nA = n1A + pend bits (or none), symbol B nB bits after
+    // it; while nA + nB <= 32 -- nearly always: a symbol settles about as many bits as its information content -- they
+    // are one number, (VA << nB) | VB, and the accumulator shift, the word-boundary test and the predicated store
+    // sequence run once for the pair instead of once per symbol.  Otherwise (a long pending run, two very rare symbols
+    // in a row) the two codes take the one-symbol path in order.  Returns the new pending count.
+    struct Code { uint32_t bits, n1, k; };
+    __device__ __forceinline__ uint32_t put_pair(const Code &A, const Code &B, uint32_t pend) {
+        const bool ea = A.n1 != 0;
+        const uint32_t na = ea ? A.n1 + pend : 0u;
+        const uint32_t pend1 = (ea ? 0u : pend) + A.k;
+        const bool eb = B.n1 != 0;
+        const uint32_t nb2 = eb ? B.n1 + pend1 : 0u;
+        if (__builtin_expect(na + nb2 > 32, 0)) {
+            (void)put_code(A.bits, A.n1, pend, A.k);
+            return put_code(B.bits, B.n1, pend1, B.k);
+        }
+        const uint32_t va = A.bits + __funnelshift_lc(0u, 1u, na - 1u) - __funnelshift_lc(0u, 1u, A.n1 - 1u);
+        const uint32_t vb = B.bits + __funnelshift_lc(0u, 1u, nb2 - 1u) - __funnelshift_lc(0u, 1u, B.n1 - 1u);
+        put(shl_c(va, nb2) | vb, na + nb2);
+        return (eb ? 0u : pend1) + B.k;
+    }
     __device__ __forceinline__ uint32_t finish() {                          // flush_bits (src/bitio/mod.rs:183-198)
         const uint32_t bytes = wi * 4 + (nb + 7) / 8;
         if (nb) w0[wi] = __byte_perm((uint32_t)(acc << (32 - nb)), 0, 0x0123);
@@ -433,6 +454,26 @@ __device__ __forceinline__ uint32_t encode_step_al(uint32_t &L, uint32_t &H, uin
     return n;
 }
 
+// The same step with the emission left to the caller (BitSink2::put_pair): returns the settled bits and the two counts.
+template <int CLS, bool C32>
+__device__ __forceinline__ BitSink2::Code encode_core_al(uint32_t &L, uint32_t &H, uint32_t cl, uint32_t ch, uint32_t count,
+                                                         const typename Cls<CLS>::M &g, uint32_t sh, uint32_t one)
+{
+    using C = Cls<CLS>;
+    using P = typename C::P;
+    const uint32_t rm1 = (H - L) >> sh;
+    const P nh = C::mulr(ch, rm1), nl = C::mulr(cl, rm1);
+    const uint32_t nh2 = ~((uint32_t)C::divc(nh, g, count) * one + (L - 1u));
+    const uint32_t l2 = (uint32_t)C::divc(nl, g, count) * one + L;
+    uint32_t n1, n;
+    renorm_counts<C32>(l2, nh2, n1, n);
+    BitSink2::Code cd;
+    cd.bits = top_bits(l2, n1); cd.n1 = n1; cd.k = n - n1;
+    L = shl_c(l2, n) & 0x7FFFFFFFu;
+    H = ~shl_c(nh2, n) | 0x80000000u;
+    return cd;
+}
+
 // ------------------------------------------------------------------ encoder
 template <typename TW, int CLS, bool FULL, bool C32>
 __global__ void __launch_bounds__(kLaneThreads, 2)
@@ -478,6 +519,13 @@ encode_lane_al_kernel(const LaneEncJob job)
         encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, count0 + t, g, sh, one);
         ++t;
     };
+    auto adapt_core = [&](uint32_t sym, const M &g) {
+        uint32_t cl, ch;
+        tab.template query<true>(sym, count0 + t - eof_freq - (FULL ? 0u : 256u), cl, ch);
+        const BitSink2::Code cd = encode_core_al<CLS, C32>(L, H, cl, ch, count0 + t, g, sh, one);
+        ++t;
+        return cd;
+    };
     auto adapt_step = [&](uint32_t sym) {
         const M g = gn;
         gn = C::ldm(magic + t + 1);
@@ -489,8 +537,11 @@ encode_lane_al_kernel(const LaneEncJob job)
         while (t + 4 <= n_adapt) {
             const M m0 = C::ldm(magic + t + 4), m1 = C::ldm(magic + t + 5), m2 = C::ldm(magic + t + 6), m3 = C::ldm(magic + t + 7);
             const uint32_t wv = src.take_word();
-            adapt_coded(__byte_perm(wv, 0, 0x4440), g0); adapt_coded(__byte_perm(wv, 0, 0x4441), g1);
-            adapt_coded(__byte_perm(wv, 0, 0x4442), g2); adapt_coded(__byte_perm(wv, 0, 0x4443), g3);
+            // the four symbols of a word go to the bit packer as two pairs (BitSink2::put_pair)
+            const BitSink2::Code c0 = adapt_core(__byte_perm(wv, 0, 0x4440), g0), c1 = adapt_core(__byte_perm(wv, 0, 0x4441), g1);
+            pend = sink.put_pair(c0, c1, pend);
+            const BitSink2::Code c2 = adapt_core(__byte_perm(wv, 0, 0x4442), g2), c3 = adapt_core(__byte_perm(wv, 0, 0x4443), g3);
+            pend = sink.put_pair(c2, c3, pend);
             g0 = m0; g1 = m1; g2 = m2; g3 = m3;
         }
         gn = g0;
@@ -514,11 +565,20 @@ encode_lane_al_kernel(const LaneEncJob job)
             encode_step_al<CLS, C32>(L, H, pend, sink, cl_cur, ch_cur, countf, gfz, sh, one);
             ++t;
         };
+        auto frozen_core = [&](uint32_t sym) {             // the same, emission left to put_pair
+            const uint32_t cl_cur = cl, ch_cur = ch;
+            tab.query_frozen(sym, cum256f, cl, ch);
+            const BitSink2::Code cd = encode_core_al<CLS, C32>(L, H, cl_cur, ch_cur, countf, gfz, sh, one);
+            ++t;
+            return cd;
+        };
         while (t < len && !src.word_aligned()) frozen_step(src.next());
         while (t + 4 <= len) {
             const uint32_t wv = src.take_word();
-            frozen_step(__byte_perm(wv, 0, 0x4440)); frozen_step(__byte_perm(wv, 0, 0x4441));
-            frozen_step(__byte_perm(wv, 0, 0x4442)); frozen_step(__byte_perm(wv, 0, 0x4443));
+            const BitSink2::Code c0 = frozen_core(__byte_perm(wv, 0, 0x4440)), c1 = frozen_core(__byte_perm(wv, 0, 0x4441));
+            pend = sink.put_pair(c0, c1, pend);
+            const BitSink2::Code c2 = frozen_core(__byte_perm(wv, 0, 0x4442)), c3 = frozen_core(__byte_perm(wv, 0, 0x4443));
+            pend = sink.put_pair(c2, c3, pend);
         }
         while (t < len) frozen_step(src.next());
         encode_step_al<CLS, C32>(L, H, pend, sink, cl, ch, countf, gfz, sh, one);
