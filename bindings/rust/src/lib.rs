@@ -43,6 +43,8 @@ extern "C" {
     pub fn redux_ctx_device_count(ctx: *const redux_ctx_t) -> c_int;
     pub fn redux_ctx_last_error(ctx: *const redux_ctx_t) -> *const c_char;
     pub fn redux_ctx_set_schedule(ctx: *mut redux_ctx_t, sched: c_int) -> c_int;
+    /// pageable caller buffers: staged through the library's pinned ring and copy threads (default) or left to the driver
+    pub fn redux_ctx_set_staging(ctx: *mut redux_ctx_t, enable: c_int, min_bytes: usize, piece_bytes: usize, slots: c_int, threads: c_int) -> c_int;
     pub fn redux_compress(ctx: *mut redux_ctx_t, model_kind: c_int, p: *const redux_params_t,
                           input: *const u8, in_len: u64, out: *mut u8, out_cap: u64,
                           in_count: *mut u64, out_count: *mut u64) -> c_int;
