@@ -3,19 +3,20 @@
 // instruction count per symbol cut where profiles/r01_final_* showed the issue slots going:
 //   * LEFT-ALIGNED coder state.  low/high (src/codec.rs:11-24) live in the top c bits of a 32-bit
 //     register (high's spare low bits are ones, low's zeros).  The closed-form renormalisation of
-//     src/codec.rs:62-89 then needs no code_bits arithmetic at all: n1 = clz(low ^ high) and
-//     k = clz(~((low & ~high) << (n1+1))) are one FLO.SH each (bfind.shiftamt; neither operand can be
-//     zero because of the spare bits), the settled bits are the top n1 bits of low (one funnel shift) and
-//     high refills with ones through a funnel shift;
+//     src/codec.rs:62-89 then needs no code_bits arithmetic at all: n1 = clz(low ^ high) and the total
+//     n1 + k = clz((low ^ high) & ~((low & ~high) << 1)) are one FLO.SH each, side by side (renorm_counts;
+//     bfind.shiftamt; neither operand can be zero because of the spare bits), the settled bits are the top
+//     n1 bits of low (one funnel shift) and high refills with ones through a funnel shift;
 //   * the decoder's code value (src/codec.rs:124-158) is a 32-bit WINDOW into the compressed stream whose
 //     top c bits are the value and whose low bits are look-ahead; E1/E2 shifts are a funnel shift that
 //     pulls the following stream bits in, E3 shifts keep the MSB and drop the bits below it -- 4
 //     instructions instead of extracting n bits and merging them;
-//   * branch-free pending-bit emission (put_bit, src/codec.rs:39-46) and a word-indexed packer;
-//   * the adaptive phase shares the Fenwick node addresses between the range query and the update
-//     (adaptive_tree.rs:63-92): node (s | (2^k-1)) + 1 of the update path is the query's node
-//     s & (0xFF << k) plus the constant 2^k, so the update is load/add/store per level with no address
-//     arithmetic, and absent query nodes are masked by value instead of by address;
+//   * branch-free pending-bit emission (put_bit, src/codec.rs:39-46) and a word-indexed packer that takes
+//     two symbols per append (BitSink2::put_pair);
+//   * the adaptive encoder loads ONE Fenwick node per tree level, which serves the range query where the
+//     symbol's bit is set and the update where it is clear (adaptive_tree.rs:63-92; LaneTable2::query);
+//   * the decoder descends four ways per round on the sign bits of residuals -- no predicates -- and, once the
+//     model is frozen, on the absolute boundaries of the cumulative array (LaneDecoderAl::step);
 //   * FULL tables (whenever the entry type can hold them): nodes store the reference's actual tree
 //     values (adaptive_tree.rs:43-45 initialises tree[i] = lowbit(i)) instead of increments, so neither
 //     the query nor the decoder's descent adds the implicit lowbit terms back.
