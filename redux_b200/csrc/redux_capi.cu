@@ -294,7 +294,7 @@ struct Plan {
 
 // REDUX_SCHED_AUTO, encode: up to this many streams the split encoder (parallel model phase + one coder warp per
 // stream) beats 32 streams per warp (profiles/r02_small_batches_corpora.json, profiles/r02_underfilled.json: 512
-// blocks of 64 KiB encode in 7.1 ms split vs 8.8 ms lane, 9.7 vs 14.0 ms at (8,30,32); 2,048 blocks 19.5 vs 9.2 ms).  The plain warp encoder never
+// blocks of 64 KiB encode in 7.1 ms split vs 7.6 ms lane, 9.7 vs 12.2 ms at (8,30,32); 2,048 blocks 19.6 vs 8.3 ms).  The plain warp encoder never
 // wins (29 corpus files: 31 MB/s against 62 lane and 86 split), so AUTO falls back to the lane mapping, not to it.
 constexpr uint64_t kWarpAutoMaxBlocks = 512;
 
