@@ -244,6 +244,9 @@ void redux_generate_blocks_host_ex(uint8_t *out, uint64_t first_block, uint64_t 
  * exact for n = cum * range < 2^49 with cum <= d). */
 int redux_debug_magic(uint64_t d, uint32_t nbits, int wide, uint64_t *magic, uint32_t *shift);
 uint64_t redux_debug_magic_divide(uint64_t n, uint64_t magic, uint32_t shift, int wide);
+/* floor(x / range) as the code_bits > 32 decoder computes it (double estimate + one remainder check); exact whenever
+ * the quotient is below 2^31 (it is a cumulative frequency: < freq_max). */
+uint32_t redux_debug_div_by_range(uint64_t x, uint64_t range);
 /* Closed-form renormalisation of one (low, high) pair: returns n1 (E1/E2 shifts) in
  * *n1 and k (E3 shifts) in *k and the renormalised pair. */
 void redux_debug_renorm(uint64_t low, uint64_t high, uint32_t code_bits,

@@ -135,6 +135,8 @@ def lib():
     L.redux_debug_magic.argtypes = [u64, u32, i32, C.POINTER(u64), C.POINTER(u32)]
     L.redux_debug_magic_divide.argtypes = [u64, u64, u32, i32]
     L.redux_debug_magic_divide.restype = u64
+    L.redux_debug_div_by_range.argtypes = [u64, u64]
+    L.redux_debug_div_by_range.restype = u32
     L.redux_debug_renorm.argtypes = [u64, u64, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64), C.POINTER(u64)]
     L.redux_debug_renorm.restype = None
     L.redux_debug_shard.argtypes = [u64, u32, u32, C.POINTER(u64), C.POINTER(u64)]

@@ -669,6 +669,8 @@ extern "C" int redux_debug_magic(uint64_t d, uint32_t nbits, int wide, uint64_t 
     return REDUX_OK;
 }
 
+extern "C" uint32_t redux_debug_div_by_range(uint64_t x, uint64_t range) { return div_by_range64(x, range); }
+
 extern "C" uint64_t redux_debug_magic_divide(uint64_t n, uint64_t magic, uint32_t shift, int wide)
 {
     if (wide == 2) { Magic64 g{magic, shift, 0}; return div_magic65(n, g); }

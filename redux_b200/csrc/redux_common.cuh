@@ -121,6 +121,21 @@ RDX_HD uint64_t div_magic65(uint64_t n, Magic64 g) {
 // otherwise n/d is at least 1/d below the next integer and 2^-19 + E = 1.5 x 2^-19 < 1/d keeps the result below it:
 // the truncation is the exact quotient, no correction step.
 // (The conversion goes through 64 bits: the quotient reaches 2^32 when cum == d and range == 2^32.)
+// floor(X / range) for the code_bits > 32 decoder: X < count * range < 2^64, so the quotient is below count <= 2^31.
+// The double quotient carries three roundings of 2^-53 relative each (two conversions, one IEEE division): it lies
+// within 2^31 * 3 * 2^-53 < 2^-20 of X / range.  Biased down by 2^-18 its truncation is the quotient or one less
+// (never more), which ONE remainder check settles; v * range <= X then, so the product cannot overflow.
+RDX_HD uint32_t div_by_range64(uint64_t X, uint64_t range) {
+#if defined(__CUDA_ARCH__)
+    const double q = __ull2double_rn(X) / __ull2double_rn(range) - 0x1p-18;
+#else
+    const double q = (double)X / (double)range - 0x1p-18;
+#endif
+    uint32_t v = q > 0.0 ? (uint32_t)q : 0u;
+    if (X - (uint64_t)v * range >= range) ++v;
+    return v;
+}
+
 struct MagicD { double r; };
 constexpr uint32_t kWideDMaxCount = 349525;                   // totals must stay BELOW this
 RDX_HD MagicD make_magicd(uint32_t d) { MagicD g; g.r = 1.0 / (double)d; return g; }

@@ -555,6 +555,37 @@ struct LaneDecoder {
                     plo = r2 ? p2 : base;
                     I += (ra ? (uint32_t)(m << 5) : 0u) + (r2 ? (uint32_t)(h << 5) : 0u);
                 }
+            } else if (CLS == kHuge) {
+                // Quotient first, as the 64-bit-product class of redux_lane_al.cuh: the reference's
+                // value = X / range (src/codec.rs:131) from a double estimate made exact by one remainder check
+                // (div_by_range64), then the 4-ary descent on plain 32-bit values in the residual domain --
+                // R = v - lo, N = v - hi < 0, each round's three sign bits move the position, unsigned min / max
+                // pick the new bounds -- with the model update on the left turns.  Four dependent table round trips
+                // of 32-bit adds instead of eight of 64-bit multiply-adds and 64-bit comparisons.
+                const uint32_t v = div_by_range64((uint64_t)X, (uint64_t)rm1 + 1u);
+                uint32_t R = v, N = v - (count - 1u);             // node 256 = count - 1
+#pragma unroll
+                for (int m = 128; m >= 2; m >>= 2) {
+                    const int h = m >> 1;
+                    const int oddadj = (h == 1) ? LaneTable<TW>::kOddAdj : 0;
+                    const uint32_t ia = I + (uint32_t)(m << 5), ib = (uint32_t)((int)I + (h << 5) + oddadj),
+                                   ic = (uint32_t)((int)I + ((m + h) << 5) + oddadj);
+                    const uint32_t ar = tab.t[ia], br = tab.t[ib], cr = tab.t[ic];
+                    const uint32_t da = R - ((uint32_t)m + ar), db = R - ((uint32_t)h + br), dc = da - ((uint32_t)h + cr);
+                    const uint32_t ma = (uint32_t)((int32_t)da >> 31), mb = (uint32_t)((int32_t)db >> 31), mc = (uint32_t)((int32_t)dc >> 31);
+                    if (ADAPT) {                                  // + 1 where the descent turns left (node c: only after a right turn)
+                        tab.t[ia] = (TW)(ar - ma);
+                        tab.t[ib] = (TW)(br - mb);
+                        tab.t[ic] = (TW)(cr - mc + ma);
+                    }
+                    const uint32_t r1 = da < dc ? da : dc, r2 = R < db ? R : db;
+                    const uint32_t n1 = da > dc ? da : dc, n2 = N > db ? N : db;
+                    R = r1 < r2 ? r1 : r2;
+                    N = n1 > n2 ? n1 : n2;
+                    I += (3u + ma + mb + mc) * (uint32_t)(h << 5);
+                }
+                plo = C::mulr(v - R, rm1);
+                phi = C::mulr(v - N, rm1);
             } else {
 #pragma unroll
                 // The model update rides on the descent (as in redux_lane_al.cuh): the nodes update(s+1) increments

@@ -137,6 +137,29 @@ def test_count_reciprocal_double_is_exact_below_its_bound():
     assert _bad_magic(top, 3)
 
 
+def test_quotient_by_range_is_exact_for_64_bit_operands():
+    """code_bits > 32 decoder: value = X / range (src/codec.rs:131) from a double estimate and one remainder check.
+    Quotients up to 2^31 - 1 (a cumulative frequency), ranges from 2^31 to 2^62, X at exact multiples, just below and
+    just above them (where a rounding error would tip the estimate), and at the top of the 64-bit range."""
+    rng = np.random.default_rng(64)
+    L = rb.lib()
+    ranges = [(1 << 31) + 1, (1 << 33) - 1, 1 << 40, (1 << 47) + 12345, (1 << 53) - 1, (1 << 53) + 1, 1 << 60, (1 << 62) - 1, 1 << 62]
+    ranges += [int(x) for x in rng.integers(1 << 31, 1 << 62, size=200, dtype=np.uint64)]
+    for r in ranges:
+        qmax = min((1 << 31) - 1, ((1 << 64) - 1) // r)
+        qs = {0, 1, 2, qmax, qmax - 1, qmax // 2, qmax // 3} | {int(x) for x in rng.integers(0, qmax + 1, size=40)}
+        for q in qs:
+            if q < 0:
+                continue
+            for x in (q * r, q * r + 1, q * r + r - 1, q * r + r // 2):
+                if x < (1 << 64):
+                    assert L.redux_debug_div_by_range(x, r) == x // r, (x, r)
+    for x in ((1 << 64) - 1, (1 << 64) - 2, (1 << 63) + 1):
+        for r in ((1 << 62), (1 << 62) - 1, (1 << 61) + 7, (1 << 40) * 3):
+            if x // r < (1 << 31):
+                assert L.redux_debug_div_by_range(x, r) == x // r, (x, r)
+
+
 def _bad_magic(d, wide):
     m, sh = C.c_uint64(), C.c_uint32()
     return rb.lib().redux_debug_magic(d, 0, wide, C.byref(m), C.byref(sh)) == rb.INVALID_INPUT

@@ -112,7 +112,8 @@ def make_blocks(rng, n, max_len):
 
 # (f, c): narrow incl. the frozen regime (f=10 freezes after 766 symbols), wide, c == 32, huge
 PARAMS = [(10, 12), (10, 16), (14, 16), (12, 18), (16, 18), (22, 24), (20, 31), (30, 32), (24, 30), (30, 34), (20, 40),
-          (10, 30), (12, 32), (10, 21)]      # 64-bit-product classes that freeze early (tree-based frozen decoder)
+          (10, 30), (12, 32), (10, 21),      # 64-bit-product classes that freeze early (tree-based frozen decoder)
+          (10, 40), (10, 54)]                 # the same with code_bits > 32 (64-bit coder state)
 
 
 @pytest.mark.parametrize("f,c", PARAMS)
