@@ -228,6 +228,26 @@ extern "C" uint32_t emu_step_al(uint32_t c, uint32_t f, uint32_t low, uint32_t h
     return n;
 }
 
+// The bit packer's pair path against its one-symbol path: a sequence of n codes (bits[i], n1[i], k[i]) from pending
+// count pend0, appended pairwise by put_pair (an odd last one by put_code) into out_pair and one by one by put_code into
+// out_single.  Returns the byte count of out_pair; *same = 1 when the bytes, lengths and final pending counts agree.
+extern "C" uint32_t emu_put_pairs(const uint32_t *bits, const uint32_t *n1, const uint32_t *k, uint32_t n, uint32_t pend0,
+                                  uint8_t *out_pair, uint8_t *out_single, int *same)
+{
+    BitSink2 a, b;
+    a.init(out_pair); b.init(out_single);
+    uint32_t pa = pend0, pb = pend0;
+    for (uint32_t i = 0; i + 1 < n; i += 2) {
+        BitSink2::Code A{bits[i], n1[i], k[i]}, B{bits[i + 1], n1[i + 1], k[i + 1]};
+        pa = a.put_pair(A, B, pa);
+    }
+    if (n & 1) pa = a.put_code(bits[n - 1], n1[n - 1], pa, k[n - 1]);
+    for (uint32_t i = 0; i < n; ++i) pb = b.put_code(bits[i], n1[i], pb, k[i]);
+    const uint32_t la = a.finish(), lb = b.finish();
+    *same = la == lb && pa == pb && memcmp(out_pair, out_single, la) == 0;
+    return la;
+}
+
 // ------------------------------------------------------------------ generic path (any symbol width, pre-trained models)
 namespace {
 struct GenericSetup { std::vector<uint32_t> init, tabs; std::vector<Magic64> magic; GenericJob job; };

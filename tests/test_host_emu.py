@@ -171,6 +171,42 @@ def test_truncated_streams_and_full_sinks(emu):
     assert all(outs[i] == b[:-1] for i, (_, b) in enumerate(nonempty))
 
 
+def test_bit_packer_pairs_equal_single_codes(emu):
+    """BitSink2::put_pair (two symbols, one append) writes the bytes of two put_code calls: random code sequences with
+    settled-bit counts 0..32, E3 runs that leave the pending count anywhere from 0 to beyond 32, so that both the
+    merged path (nA + nB <= 32) and its in-order fallback are taken, at every accumulator phase."""
+    emu.emu_put_pairs.argtypes = [C.c_void_p] * 3 + [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    emu.emu_put_pairs.restype = C.c_uint32
+    rng = np.random.default_rng(2)
+    fallback = merged = 0
+    for trial in range(400):
+        n = int(rng.integers(1, 60))
+        wide = trial % 4 == 0                                  # every fourth trial: long codes and long pending runs
+        n1 = rng.integers(0, 33 if wide else 12, n).astype(np.uint32)
+        n1[rng.random(n) < 0.2] = 0
+        k = np.where(rng.random(n) < 0.3, rng.integers(0, 40 if wide else 6, n), 0).astype(np.uint32)
+        bits = np.array([int(rng.integers(0, 1 << int(x))) if x else 0 for x in n1], dtype=np.uint32)
+        pend0 = int(rng.integers(0, 35)) if wide else int(rng.integers(0, 3))
+        cap = 8 * (int(n1.sum()) + int(k.sum()) + pend0) // 8 + 64
+        a = np.zeros(cap + 64, dtype=np.uint8); b = np.zeros(cap + 64, dtype=np.uint8)
+        # 16-byte aligned slots, as the kernels' (word stores)
+        oa = (-a.ctypes.data) % 16; ob = (-b.ctypes.data) % 16
+        same = C.c_int(0)
+        la = emu.emu_put_pairs(bits.ctypes.data, n1.ctypes.data, k.ctypes.data, n, pend0, a.ctypes.data + oa, b.ctypes.data + ob, C.byref(same))
+        assert same.value == 1, (trial, n, la)
+        # which path the pairs took (for the coverage assertion below)
+        pend = pend0
+        for i in range(0, n - 1, 2):
+            na = int(n1[i]) + pend if n1[i] else 0
+            pend1 = (0 if n1[i] else pend) + int(k[i])
+            nb = int(n1[i + 1]) + pend1 if n1[i + 1] else 0
+            pend = (0 if n1[i + 1] else pend1) + int(k[i + 1])
+            if na + nb > 32: fallback += 1
+            else: merged += 1
+        # (an odd last code does not change pend's role here)
+    assert fallback > 50 and merged > 1000, (fallback, merged)
+
+
 def test_long_pending_runs(emu):
     """Inputs alternating around the interval midpoint keep the coder in E3 shifts (src/codec.rs:75-83; pending
     runs of ~10 bits here).  Runs far beyond 32 bits -- the packers' slow paths -- come from the adversarial
